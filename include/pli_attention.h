@@ -1,0 +1,168 @@
+/*
+ * pli_attention.h — C ABI of the B200-native attention hot path.
+ *
+ * This is the drop-in boundary for the one data-parallel path of
+ * Infatoshi/physics-llm-inference that this repository rebuilds:
+ * chapter 6's tiled FlashAttention forward, with chapter 1's causal mask and GQA head map,
+ * and the decode-time read of the chapter 2 contiguous KV cache / chapter 7 paged KV blocks.
+ *
+ * The reference has no FFI of its own: its boundary is the Python function
+ * `flash_attention_forward(q, k, v, scale=None, config=None)`.  Each entry point below names
+ * the reference code (path:line under /root/reference) whose arithmetic it replaces.  The Python
+ * host side (`physics_llm_inference_b200/`) binds these symbols with ctypes and keeps the
+ * reference's call signature; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated;
+ *   - strides are in ELEMENTS; the innermost (head_dim) stride is always 1;
+ *   - the caller owns every buffer (outputs, workspace); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous, no host sync, safe
+ *     under CUDA-graph capture;
+ *   - return value 0 = success, negative = error (`pli_last_error()` gives the text; errors are
+ *     thread-local).  Nothing throws across the ABI.  There is no CPU fallback.
+ */
+#ifndef PLI_ATTENTION_H_
+#define PLI_ATTENTION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLI_ABI_VERSION 1
+
+/* element types of q/k/v/o and of the KV storage */
+#define PLI_BF16 0
+#define PLI_F16 1
+#define PLI_F32 2
+
+/* error codes */
+#define PLI_OK 0
+#define PLI_ERR_INVALID (-1)      /* bad shape / dtype / alignment / argument            */
+#define PLI_ERR_UNSUPPORTED (-2)  /* valid request this build has no kernel for          */
+#define PLI_ERR_CUDA (-3)         /* a CUDA runtime / driver call failed                 */
+#define PLI_ERR_DEVICE (-4)       /* current device is not sm_100 (B200)                 */
+
+/* which kernel family served a request (reported by pli_*_kernel_kind) */
+#define PLI_KIND_NONE 0
+#define PLI_KIND_TCGEN05 1 /* TMA + tcgen05.mma + TMEM, bf16/f16, head_dim 64/128       */
+#define PLI_KIND_SIMT 2    /* CUDA-core fp32-accumulate kernel: f32 inputs, odd head_dim */
+#define PLI_KIND_MMA_TMA 3 /* decode: TMA page loads + mma.sync, bf16/f16                */
+
+int pli_abi_version(void);
+const char* pli_last_error(void);
+
+/* Make `device` current for this library's CUDA runtime (the host side calls it next to
+ * torch.cuda.device(...), so both runtimes agree).  Also checks that the device is sm_100. */
+int pli_set_device(int device);
+
+/* Number of kernels this library has launched on the calling thread since load (or since the
+ * last pli_reset_launch_count).  bench.py reports it as `gpu_launches`. */
+uint64_t pli_launch_count(void);
+void pli_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Prefill / full attention forward.
+ *
+ * Replaces ch06/flash_attention.py:14-74 (`flash_attention_forward`: S = QK^T*scale :55,
+ * online-softmax rescale :57-62, O update :64-65), with
+ *   - GQA head map of ch01/gqa.py:14,30-31: q-head h reads kv-head h / (Hq/Hkv);
+ *   - causal rule of ch01/gqa.py:33-34 and ch02/cached_generation.py:85-91: key j is visible to
+ *     query i iff j <= i + (Nk - Nq) (bottom-right aligned; requires Nq <= Nk);
+ *   - log-sum-exp per row (the reference computes row_max/row_sum at :71-72 and drops them).
+ *
+ *   q  (B,Hq,Nq,D)   k,v (B,Hkv,Nk,D)   o (B,Hq,Nq,D) same dtype as q   lse (B,Hq,Nq) f32 or NULL
+ *   *_strides[3] = {batch, head, token} element strides; head_dim stride is 1.
+ *   bf16/f16 with D in {64,128}: tcgen05 kernel (needs 16-byte aligned pointers and strides that
+ *   are multiples of 8 elements).  Anything else with D <= 256: SIMT kernel.
+ * ------------------------------------------------------------------------------------------- */
+int pli_prefill_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                    int B, int Hq, int Hkv, int Nq, int Nk, int D,
+                    const int64_t q_strides[3], const int64_t k_strides[3],
+                    const int64_t v_strides[3], const int64_t o_strides[3],
+                    float scale, int causal, int dtype, void* stream);
+
+/* Which kernel pli_prefill_fwd would use for this problem (PLI_KIND_*), without launching. */
+int pli_prefill_kernel_kind(int D, int dtype, const int64_t q_strides[3], const int64_t k_strides[3],
+                            const int64_t v_strides[3], const int64_t o_strides[3],
+                            const void* q, const void* k, const void* v, const void* o);
+
+/* ---------------------------------------------------------------------------------------------
+ * Decode: one query token per sequence over a KV cache, split-KV + log-sum-exp combine.
+ *
+ * Replaces the attention block of ch02/cached_generation.py:72-94 (`CachedGQA.forward`; same
+ * maths at ch02/kv_cache.py:81-98) for seq_len == 1 (no mask, :85), reading either
+ *   - the contiguous cache of ch02/kv_cache.py:25-34 / ch02/cached_generation.py:23
+ *       (B, max_seq_len, Hkv, D), block_table == NULL; or
+ *   - the paged pools of ch07/paged_memory.py:38-48 (num_blocks, num_layers, block_size, Hkv, D)
+ *     through a block table (ch07/paged_memory.py:7-13): logical token t of sequence b lives in
+ *     page block_table[b*table_stride + t / block_size], slot t % block_size (ceil-div rule of
+ *     ch07/paged_memory.py:54,84-86).  Tokens >= seq_lens[b] are never read as values.
+ *
+ *   q (B,Hq,D) with strides {batch, head};  o (B,Hq,D) same dtype;  lse (B,Hq) f32 or NULL.
+ *   kv_strides[4] = element strides of the K/V storage:
+ *       paged:       {page, layer, slot, head}      contiguous: {batch, 0, token, head}
+ *   kv_extent = number of pages in the pool (paged) or B (contiguous): bounds for TMA descriptors.
+ *   max_seq_len = upper bound of seq_lens (host value; no device sync is done to find it).
+ *   num_splits  = KV splits per (b, kv head); pass 0 to let the library pick
+ *                 (pli_decode_num_splits); workspace must hold pli_decode_workspace_bytes().
+ *
+ * pli_decode_fwd = pli_decode_splitkv (partials into workspace) + pli_decode_combine.
+ * ------------------------------------------------------------------------------------------- */
+int pli_decode_num_splits(int B, int Hkv, int max_seq_len);
+size_t pli_decode_workspace_bytes(int B, int Hq, int D, int num_splits);
+
+int pli_decode_splitkv(const void* q, const void* k_store, const void* v_store,
+                       const int32_t* block_table, const int32_t* seq_lens,
+                       int B, int Hq, int Hkv, int D, int max_seq_len,
+                       int block_size, int table_stride, int layer, int64_t kv_extent,
+                       const int64_t q_strides[2], const int64_t kv_strides[4],
+                       float scale, int dtype, int num_splits,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+int pli_decode_combine(const void* workspace, void* o, float* lse,
+                       int B, int Hq, int D, int num_splits,
+                       const int64_t o_strides[2], int dtype, void* stream);
+
+int pli_decode_fwd(const void* q, const void* k_store, const void* v_store,
+                   const int32_t* block_table, const int32_t* seq_lens,
+                   void* o, float* lse,
+                   int B, int Hq, int Hkv, int D, int max_seq_len,
+                   int block_size, int table_stride, int layer, int64_t kv_extent,
+                   const int64_t q_strides[2], const int64_t kv_strides[4], const int64_t o_strides[2],
+                   float scale, int dtype, int num_splits,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+int pli_decode_kernel_kind(int D, int dtype, int block_size, const int64_t kv_strides[4],
+                           const void* k_store, const void* v_store);
+
+/* ---------------------------------------------------------------------------------------------
+ * KV-cache write path: append n new tokens per sequence.
+ *
+ * Replaces the slice-assign of ch02/kv_cache.py:45-46 / ch02/cached_generation.py:30-31
+ * (`cache[:, seq_len:seq_len+n] = new`) and, for pages, the write that
+ * ch07/paged_memory.py:76-98 (`extend_blocks`) makes room for.
+ *
+ *   k_new,v_new (B, n, Hkv, D) with new_strides {batch, token, head};
+ *   start_pos (B,) int32: position of the first new token per sequence (device);
+ *   storage / block_table / kv_strides as for decode.
+ * ------------------------------------------------------------------------------------------- */
+int pli_kv_append(const void* k_new, const void* v_new, void* k_store, void* v_store,
+                  const int32_t* block_table, const int32_t* start_pos,
+                  int B, int n_new, int Hkv, int D,
+                  int block_size, int table_stride, int layer,
+                  const int64_t new_strides[3], const int64_t kv_strides[4],
+                  int dtype, void* stream);
+
+/* Debug / parity aid: gather one layer of paged K (or V) into a contiguous (B, max_len, Hkv, D)
+ * buffer with the kernel-side address rule, so tests can assert page indexing bit-exactly. */
+int pli_paged_gather(const void* store, void* out, const int32_t* block_table, const int32_t* seq_lens,
+                     int B, int max_len, int Hkv, int D, int block_size, int table_stride, int layer,
+                     const int64_t kv_strides[4], int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLI_ATTENTION_H_ */

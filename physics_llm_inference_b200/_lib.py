@@ -1,0 +1,117 @@
+"""ctypes binding of the C ABI in include/pli_attention.h (libpli_attention.so).
+
+There is no CPU fallback: if the library is missing or a call fails, the caller gets an exception.
+The library is built in-tree by `physics_llm_inference_b200.build` / `__graft_entry__.build()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libpli_attention.so")
+HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "pli_attention.h")
+
+PLI_BF16, PLI_F16, PLI_F32 = 0, 1, 2
+PLI_KIND_NONE, PLI_KIND_TCGEN05, PLI_KIND_SIMT, PLI_KIND_MMA_TMA = 0, 1, 2, 3
+KIND_NAMES = {0: "none", 1: "tcgen05", 2: "simt", 3: "mma_tma"}
+
+_I64P = C.POINTER(C.c_int64)
+_VP = C.c_void_p
+
+_SIGNATURES = {
+    "pli_abi_version": (C.c_int, []),
+    "pli_last_error": (C.c_char_p, []),
+    "pli_set_device": (C.c_int, [C.c_int]),
+    "pli_launch_count": (C.c_uint64, []),
+    "pli_reset_launch_count": (None, []),
+    "pli_prefill_fwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  _I64P, _I64P, _I64P, _I64P, C.c_float, C.c_int, C.c_int, _VP]),
+    "pli_prefill_kernel_kind": (C.c_int, [C.c_int, C.c_int, _I64P, _I64P, _I64P, _I64P, _VP, _VP, _VP, _VP]),
+    "pli_decode_num_splits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "pli_decode_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pli_decode_splitkv": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int64, _I64P, _I64P, C.c_float, C.c_int, C.c_int, _VP,
+                                     C.c_size_t, _VP]),
+    "pli_decode_combine": (C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _I64P, C.c_int, _VP]),
+    "pli_decode_fwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_float, C.c_int,
+                                 C.c_int, _VP, C.c_size_t, _VP]),
+    "pli_decode_kernel_kind": (C.c_int, [C.c_int, C.c_int, C.c_int, _I64P, _VP, _VP]),
+    "pli_kv_append": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_int, _I64P, _I64P, C.c_int, _VP]),
+    "pli_paged_gather": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   _I64P, C.c_int, _VP]),
+    # debug aid, not declared in the public header
+    "pli_debug_umma_selftest": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
+}
+
+_lib = None
+
+
+class PliError(RuntimeError):
+    """A C-ABI call returned a non-zero code."""
+
+
+def header_symbols() -> list[str]:
+    """Every function name declared in include/pli_attention.h."""
+    with open(HEADER_PATH) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(pli_[a-z0-9_]+)\s*\(", text)))
+
+
+def load() -> C.CDLL:
+    """Load libpli_attention.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PliError(
+            f"{LIB_PATH} is missing: build it with `python -m physics_llm_inference_b200.build` "
+            "(there is no CPU fallback for the attention path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pli_abi_version() != 1:
+        raise PliError(f"ABI version mismatch: library reports {lib.pli_abi_version()}, binding expects 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().pli_last_error().decode("utf-8", "replace")
+        if rc == -1:
+            raise ValueError(f"pli: {msg}")
+        raise PliError(f"pli error {rc}: {msg}")
+
+
+def i64(*vals) -> C.Array:
+    return (C.c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def dtype_code(dtype) -> int:
+    import torch
+    if dtype == torch.bfloat16:
+        return PLI_BF16
+    if dtype == torch.float16:
+        return PLI_F16
+    if dtype == torch.float32:
+        return PLI_F32
+    raise TypeError(f"unsupported dtype {dtype}: the attention path takes bfloat16, float16 or float32")
+
+
+def current_stream_ptr(device) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().pli_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().pli_reset_launch_count()

@@ -1,0 +1,746 @@
+// decode.cu — split-KV decode attention over the ch02 contiguous cache / ch07 paged pools,
+// the log-sum-exp combine pass, the KV append (write path) and the page-gather parity aid.
+//
+// Maths: ch02/cached_generation.py:72-94 for seq_len == 1 (no mask, :85) with the GQA map of
+// :77-78.  Addressing: ch07/paged_memory.py:38-48 pool layout, token t -> page table[t / bs],
+// slot t % bs (ceil-div rule, :54,:84-86).  HBM-bound: each K/V byte is read exactly once and all
+// q heads of a KV group are served from that one read.
+//
+// Two split-KV kernels write (normalised O, natural-log LSE) partials to the workspace:
+//   decode_tma_kernel   bf16/f16, head_dim 64/128, page size 2^k in [8,256] (or contiguous):
+//                       a producer warp streams 64-token K/V stages into a 128B-swizzled smem ring
+//                       with TMA (one box per page, page ids from the block table), four consumer
+//                       warps run QK^T and PV on mma.sync m16n8k16 via ldmatrix, fp32 softmax state.
+//   decode_simt_kernel  everything else (f32 storage, odd head_dim / page size): CUDA cores.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace pli {
+namespace {
+
+// Tokens [t0, t1) of sequence length L handled by split s of S (multiples of 64; may be empty).
+__host__ __device__ __forceinline__ void split_range(int L, int S, int s, int& t0, int& t1) {
+    int chunk = (((L + S - 1) / S) + 63) & ~63;
+    t0 = min(L, s * chunk);
+    t1 = min(L, t0 + chunk);
+}
+
+__device__ __forceinline__ int64_t token_offset(const int32_t* __restrict__ table, int b, int t, int bs,
+                                                int table_stride, int layer, int hk, int64_t s_page,
+                                                int64_t s_layer, int64_t s_slot, int64_t s_head) {
+    if (table != nullptr) {
+        const int page = table[(int64_t)b * table_stride + t / bs];
+        return page * s_page + layer * s_layer + (int64_t)(t % bs) * s_slot + hk * s_head;
+    }
+    return b * s_page + (int64_t)t * s_slot + hk * s_head;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT split-KV kernel (generic)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int kDC>
+__global__ void __launch_bounds__(128) decode_simt_kernel(
+    const T* __restrict__ q, const T* __restrict__ ks, const T* __restrict__ vs,
+    const int32_t* __restrict__ table, const int32_t* __restrict__ seq_lens, int Hq, int Hkv, int D, int bs,
+    int table_stride, int layer, int64_t qsb, int64_t qsh, int64_t s_page, int64_t s_layer, int64_t s_slot,
+    int64_t s_head, float scale, int S, float* __restrict__ o_part, float* __restrict__ lse_part) {
+    __shared__ float sm_m[4], sm_d[4];
+    extern __shared__ float sm_acc[];  // [4][D]
+    const int s = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hk = h / (Hq / Hkv);
+    int t0, t1;
+    split_range(seq_lens[b], S, s, t0, t1);
+
+    float qv[kDC], acc[kDC];
+#pragma unroll
+    for (int c = 0; c < kDC; ++c) {
+        const int d = lane + 32 * c;
+        qv[c] = d < D ? to_f32<T>(q[b * qsb + h * qsh + d]) : 0.f;
+        acc[c] = 0.f;
+    }
+    float m = -INFINITY, dsum = 0.f;
+    for (int t = t0 + warp; t < t1; t += 4) {
+        const int64_t off = token_offset(table, b, t, bs, table_stride, layer, hk, s_page, s_layer, s_slot, s_head);
+        float kv[kDC], vv[kDC];
+#pragma unroll
+        for (int c = 0; c < kDC; ++c) {
+            const int d = lane + 32 * c;
+            kv[c] = d < D ? to_f32<T>(ks[off + d]) : 0.f;
+            vv[c] = d < D ? to_f32<T>(vs[off + d]) : 0.f;
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < kDC; ++c) dot = fmaf(qv[c], kv[c], dot);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o2);
+        const float sv = dot * scale;
+        const float m_new = fmaxf(m, sv);
+        const float alpha = (m == -INFINITY) ? 0.f : expf(m - m_new);
+        const float p = expf(sv - m_new);
+        dsum = dsum * alpha + p;
+#pragma unroll
+        for (int c = 0; c < kDC; ++c) acc[c] = fmaf(p, vv[c], acc[c] * alpha);
+        m = m_new;
+    }
+    if (lane == 0) {
+        sm_m[warp] = m;
+        sm_d[warp] = dsum;
+    }
+#pragma unroll
+    for (int c = 0; c < kDC; ++c)
+        if (lane + 32 * c < D) sm_acc[warp * D + lane + 32 * c] = acc[c];
+    __syncthreads();
+    float M = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
+    float w[4], den = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        w[i] = (sm_m[i] == -INFINITY) ? 0.f : expf(sm_m[i] - M);
+        den += w[i] * sm_d[i];
+    }
+    const int64_t row = ((int64_t)b * Hq + h) * S + s;
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    for (int d = threadIdx.x; d < D; d += 128) {
+        float o = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o += w[i] * sm_acc[i * D + d];
+        o_part[row * D + d] = o * inv;
+    }
+    if (threadIdx.x == 0) lse_part[row] = den > 0.f ? M + logf(den) : -INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA + mma.sync split-KV kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kStageTokens = 64;   // tokens per pipeline stage (16 per consumer warp)
+constexpr int kDecodeStages = 3;   // smem ring depth (3 x 32 KB at D=128 -> 2 CTAs per SM)
+constexpr int kConsumerWarps = 4;
+constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+template <bool kBf16>
+__device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    if constexpr (kBf16) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+            "{%0,%1,%2,%3};\n"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    } else {
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+            "{%0,%1,%2,%3};\n"
+            : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+    }
+}
+
+// byte offset of (row, 16-byte chunk) inside a [rows][64 el] 128B-swizzled sub-tile
+__device__ __forceinline__ uint32_t sw128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+struct DecodeTmaParams {
+    const void* q;
+    const int32_t* table;
+    const int32_t* seq_lens;
+    float* o_part;
+    float* lse_part;
+    int64_t qsb, qsh;
+    int Hq, Hkv, G, bs, table_stride, layer, S, box_tokens;
+    float scale_log2;
+};
+
+template <int kD, bool kBf16, bool kRows16>
+__global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid_constant__ CUtensorMap map_k,
+                                                                    const __grid_constant__ CUtensorMap map_v,
+                                                                    const DecodeTmaParams p) {
+    constexpr int kHalves = kD / 64;
+    constexpr int kSubTile = kStageTokens * 128;              // bytes of one [64 tok][64 el] sub-tile
+    constexpr int kTileBytes = kHalves * kSubTile;            // K (or V) bytes per stage
+    constexpr int kNT = kD / 8;                               // PV n-tiles
+    constexpr int kRowSlots = kRows16 ? 2 : 1;
+    using elem_t = typename std::conditional<kBf16, __nv_bfloat16, __half>::type;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* k_tiles = smem;                                  // [stages][kTileBytes]
+    uint8_t* v_tiles = smem + kDecodeStages * kTileBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(v_tiles + kDecodeStages * kTileBytes);
+    uint64_t* empty_bar = full_bar + kDecodeStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x, b = blockIdx.z;
+    const int hk = blockIdx.y % p.Hkv, hchunk = blockIdx.y / p.Hkv;   // hchunk: 16-row groups when G > 16
+    int t0, t1;
+    split_range(p.seq_lens[b], p.S, s, t0, t1);
+    const int n_stages = (t1 - t0 + kStageTokens - 1) / kStageTokens;
+    const int rows_here = min(p.G - hchunk * 16, kRows16 ? 16 : 8);
+    const int h_base = hk * p.G + hchunk * 16;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDecodeStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], kConsumerWarps);
+        }
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ===================== producer warp: TMA page loads =====================
+        if (n_stages > 0) {
+            if (lane == 0) {
+                prefetch_tensormap(&map_k);
+                prefetch_tensormap(&map_v);
+            }
+            const int boxes = kStageTokens / p.box_tokens;     // boxes (pages or sub-pages) per stage
+            const bool paged = p.table != nullptr;
+            // lane i < boxes owns box i of every stage; its page id is fetched one stage ahead
+            auto page_of = [&](int it) -> int {
+                const int t = t0 + it * kStageTokens + lane * p.box_tokens;
+                if (!paged || lane >= boxes || t >= t1) return 0;
+                return p.table[(int64_t)b * p.table_stride + t / p.bs];
+            };
+            int page_next = page_of(0);
+            for (int it = 0; it < n_stages; ++it) {
+                const int slot = it % kDecodeStages;
+                const uint32_t parity = ((it / kDecodeStages) & 1) ^ 1;
+                const int page = page_next;
+                if (it + 1 < n_stages) page_next = page_of(it + 1);
+                mbar_wait(&empty_bar[slot], parity);
+                // boxes that start at or beyond t1 are not loaded; consumers never read their smem as values
+                const int remaining = t1 - (t0 + it * kStageTokens);
+                const int live_boxes = min(boxes, (remaining + p.box_tokens - 1) / p.box_tokens);
+                if (lane == 0)
+                    mbar_arrive_expect_tx(&full_bar[slot], 2 * kHalves * live_boxes * p.box_tokens * 128);
+                __syncwarp();
+                if (lane < live_boxes) {
+                    const int t = t0 + it * kStageTokens + lane * p.box_tokens;
+                    // coordinates (d, head, slot, X, Y): paged (.., t % bs, layer, page); contiguous (.., t, 0, b)
+                    const int c2 = paged ? t % p.bs : t;
+                    const int c3 = paged ? p.layer : 0;
+                    const int c4 = paged ? page : b;
+#pragma unroll
+                    for (int hf = 0; hf < kHalves; ++hf) {
+                        const int dst = slot * kTileBytes + hf * kSubTile + lane * p.box_tokens * 128;
+                        tma_load_5d(k_tiles + dst, &map_k, &full_bar[slot], hf * 64, hk, c2, c3, c4);
+                        tma_load_5d(v_tiles + dst, &map_v, &full_bar[slot], hf * 64, hk, c2, c3, c4);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== consumer warps =====================
+        const int g0 = lane >> 2;            // row (q head within the group) of c0,c1 / a0,a1,a4,a5
+        const int qd = (lane & 3) * 2;       // column pair inside an 8-wide tile
+        // Q A-fragments for every k-step; rows >= rows_here are zero
+        uint32_t qa[kD / 16][4];
+        {
+            const elem_t* qp = reinterpret_cast<const elem_t*>(p.q) + b * p.qsb;
+#pragma unroll
+            for (int ks = 0; ks < kD / 16; ++ks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = g0 + ((j & 1) ? 8 : 0);
+                    const int col = ks * 16 + qd + ((j & 2) ? 8 : 0);
+                    uint32_t val = 0;
+                    if (row < rows_here && (kRows16 || !(j & 1)))
+                        val = *reinterpret_cast<const uint32_t*>(qp + (h_base + row) * p.qsh + col);
+                    qa[ks][j] = val;
+                }
+            }
+        }
+        float m_run[kRowSlots], d_run[kRowSlots];
+        float acc[kNT][4];
+#pragma unroll
+        for (int r = 0; r < kRowSlots; ++r) {
+            m_run[r] = -INFINITY;
+            d_run[r] = 0.f;
+        }
+#pragma unroll
+        for (int n = 0; n < kNT; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+
+        const uint32_t k_base = smem_u32(k_tiles), v_base = smem_u32(v_tiles);
+        // ldmatrix lane roles: matrix id = lane / 8, row inside the matrix = lane % 8
+        const int lm = lane >> 3, lr = lane & 7;
+        const int k_row = warp * 16 + ((lm & 2) ? 8 : 0) + lr;   // K: matrices {0,1} tokens 0-7, {2,3} tokens 8-15
+        const int k_chk = (lm & 1);                              //    matrices {0,2} chunk kc, {1,3} chunk kc+1
+        const int v_row = warp * 16 + ((lm & 1) ? 8 : 0) + lr;   // V: matrices {0,2} tokens 0-7, {1,3} tokens 8-15
+        const int v_chk = (lm >> 1);                             //    matrices {0,1} chunk nc, {2,3} chunk nc+1
+
+        for (int it = 0; it < n_stages; ++it) {
+            const int slot = it % kDecodeStages;
+            mbar_wait(&full_bar[slot], (it / kDecodeStages) & 1);
+            const int tok_base = t0 + it * kStageTokens + warp * 16;
+            const int n_valid = t1 - tok_base;                   // valid tokens in this warp's 16
+            if (n_valid > 0) {
+                // ---- S = Q K^T : 16 rows x 16 tokens ----
+                float sacc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+                for (int ks = 0; ks < kD / 16; ++ks) {
+                    const int hf = ks / 4, chunk = (ks % 4) * 2 + k_chk;
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(k_base + slot * kTileBytes + hf * kSubTile + sw128(k_row, chunk), b0, b1, b2, b3);
+                    mma16816<kBf16>(sacc[0], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+                    mma16816<kBf16>(sacc[1], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b2, b3);
+                }
+                // ---- online softmax (log2 domain), rows g0 (+8) ----
+                uint32_t pa[4];
+#pragma unroll
+                for (int r = 0; r < kRowSlots; ++r) {
+                    float sv[4] = {sacc[0][2 * r], sacc[0][2 * r + 1], sacc[1][2 * r], sacc[1][2 * r + 1]};
+                    if (n_valid < 16) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int tk = (j >> 1) * 8 + qd + (j & 1);
+                            if (tk >= n_valid) sv[j] = -INFINITY;
+                        }
+                    }
+                    float mx = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    const float m_new = fmaxf(m_run[r], mx);
+                    const float ms = m_new * p.scale_log2;
+                    const float alpha = ex2_approx(m_run[r] * p.scale_log2 - ms);   // m_run = -inf -> 0
+                    float pv[4], psum = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        pv[j] = ex2_approx(fmaf(sv[j], p.scale_log2, -ms));
+                        psum += pv[j];
+                    }
+                    psum += __shfl_xor_sync(0xffffffffu, psum, 1);
+                    psum += __shfl_xor_sync(0xffffffffu, psum, 2);
+                    d_run[r] = d_run[r] * alpha + psum;
+                    m_run[r] = m_new;
+                    if (alpha != 1.f) {
+#pragma unroll
+                        for (int n = 0; n < kNT; ++n) {
+                            acc[n][2 * r] *= alpha;
+                            acc[n][2 * r + 1] *= alpha;
+                        }
+                    }
+                    pa[r] = pack2<kBf16>(pv[0], pv[1]);          // a0a1 (r=0) / a2a3 (r=1): tokens 0-7
+                    pa[2 + r] = pack2<kBf16>(pv[2], pv[3]);      // a4a5 / a6a7: tokens 8-15
+                }
+                if (!kRows16) pa[1] = pa[3] = 0u;
+                // ---- O += P V : 16 rows x kD ----
+#pragma unroll
+                for (int nt = 0; nt < kNT; nt += 2) {
+                    const int hf = nt / 8, chunk = (nt % 8) + v_chk;
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(v_base + slot * kTileBytes + hf * kSubTile + sw128(v_row, chunk), b0, b1, b2, b3);
+                    if (n_valid < 16) {  // never multiply by storage beyond seq_len (it may hold anything)
+                        auto keep = [&](uint32_t x, int tk) -> uint32_t {
+                            return tk >= n_valid ? 0u : (tk + 1 >= n_valid ? (x & 0xFFFFu) : x);
+                        };
+                        b0 = keep(b0, qd);
+                        b1 = keep(b1, qd + 8);
+                        b2 = keep(b2, qd);
+                        b3 = keep(b3, qd + 8);
+                    }
+                    mma16816<kBf16>(acc[nt], pa[0], pa[1], pa[2], pa[3], b0, b1);
+                    mma16816<kBf16>(acc[nt + 1], pa[0], pa[1], pa[2], pa[3], b2, b3);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);
+        }
+
+        // ---- merge the four warps' partial softmax states through smem ----
+        named_bar_sync(1, kConsumerWarps * 32);                  // every stage consumed: ring is reusable
+        float* mg_m = reinterpret_cast<float*>(smem);            // [4 warps][16 rows]
+        float* mg_d = mg_m + 64;
+        float* mg_o = mg_d + 64;                                 // [4 warps][16 rows][kD]
+        if ((lane & 3) == 0) {
+#pragma unroll
+            for (int r = 0; r < kRowSlots; ++r) {
+                mg_m[warp * 16 + g0 + 8 * r] = m_run[r] * p.scale_log2;
+                mg_d[warp * 16 + g0 + 8 * r] = d_run[r];
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < kNT; ++n) {
+#pragma unroll
+            for (int r = 0; r < kRowSlots; ++r) {
+                float2 val = make_float2(acc[n][2 * r], acc[n][2 * r + 1]);
+                *reinterpret_cast<float2*>(&mg_o[(warp * 16 + g0 + 8 * r) * kD + n * 8 + qd]) = val;
+            }
+        }
+        named_bar_sync(1, kConsumerWarps * 32);
+        const int tid = threadIdx.x;                             // 0..127
+        for (int idx = tid; idx < rows_here * kD; idx += kConsumerWarps * 32) {
+            const int row = idx / kD, d = idx - row * kD;
+            float M = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) M = fmaxf(M, mg_m[w * 16 + row]);
+            float den = 0.f, o = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float mw = mg_m[w * 16 + row];
+                const float wt = (mw == -INFINITY) ? 0.f : ex2_approx(mw - M);
+                den += wt * mg_d[w * 16 + row];
+                o += wt * mg_o[(w * 16 + row) * kD + d];
+            }
+            const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
+            p.o_part[prow * kD + d] = den > 0.f ? o / den : 0.f;
+            if (d == 0) p.lse_part[prow] = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine: merge S partials per (b, q head)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) decode_combine_kernel(const float* __restrict__ o_part,
+                                                             const float* __restrict__ lse_part, T* __restrict__ o,
+                                                             float* __restrict__ lse, int Hq, int D, int S,
+                                                             int64_t osb, int64_t osh) {
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int64_t row = ((int64_t)b * Hq + h) * S;
+    float M = -INFINITY;
+    for (int s = 0; s < S; ++s) M = fmaxf(M, lse_part[row + s]);
+    float den = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float l = lse_part[row + s];
+        den += (l == -INFINITY) ? 0.f : __expf(l - M);
+    }
+    const float inv = den > 0.f ? 1.f / den : 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) {
+            const float l = lse_part[row + s];
+            const float w = (l == -INFINITY) ? 0.f : __expf(l - M);
+            acc = fmaf(w, o_part[(row + s) * D + d], acc);
+        }
+        o[b * osb + h * osh + d] = from_f32<T>(acc * inv);
+    }
+    if (lse != nullptr && threadIdx.x == 0) lse[(int64_t)b * Hq + h] = den > 0.f ? M + logf(den) : -INFINITY;
+}
+
+// ------------------------------------------------------------------------------------------------
+// KV append + page gather (16-byte vectors when aligned, else elementwise)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void kv_append_kernel(const T* __restrict__ k_new, const T* __restrict__ v_new, T* __restrict__ k_store,
+                                 T* __restrict__ v_store, const int32_t* __restrict__ table,
+                                 const int32_t* __restrict__ start_pos, int n_new, int Hkv, int D, int bs,
+                                 int table_stride, int layer, int64_t nsb, int64_t nst, int64_t nsh, int64_t s_page,
+                                 int64_t s_layer, int64_t s_slot, int64_t s_head, int vec) {
+    const int b = blockIdx.z, i = blockIdx.y;                    // sequence, new-token index
+    const int t = start_pos[b] + i;
+    const int per_tok = Hkv * (D / vec);
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per_tok; e += gridDim.x * blockDim.x) {
+        const int hk = e / (D / vec), dv = (e - hk * (D / vec)) * vec;
+        const int64_t src = b * nsb + i * nst + hk * nsh + dv;
+        const int64_t dst = token_offset(table, b, t, bs, table_stride, layer, hk, s_page, s_layer, s_slot, s_head) + dv;
+        if (vec * sizeof(T) == 16) {
+            *reinterpret_cast<uint4*>(k_store + dst) = *reinterpret_cast<const uint4*>(k_new + src);
+            *reinterpret_cast<uint4*>(v_store + dst) = *reinterpret_cast<const uint4*>(v_new + src);
+        } else {
+            k_store[dst] = k_new[src];
+            v_store[dst] = v_new[src];
+        }
+    }
+}
+
+template <typename T>
+__global__ void paged_gather_kernel(const T* __restrict__ store, T* __restrict__ out,
+                                    const int32_t* __restrict__ table, const int32_t* __restrict__ seq_lens,
+                                    int max_len, int Hkv, int D, int bs, int table_stride, int layer, int64_t s_page,
+                                    int64_t s_layer, int64_t s_slot, int64_t s_head) {
+    const int b = blockIdx.z, t = blockIdx.y;
+    const bool live = t < seq_lens[b];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < Hkv * D; e += gridDim.x * blockDim.x) {
+        const int hk = e / D, d = e - hk * D;
+        T val = from_f32<T>(0.f);
+        if (live) val = store[token_offset(table, b, t, bs, table_stride, layer, hk, s_page, s_layer, s_slot, s_head) + d];
+        out[(((int64_t)b * max_len + t) * Hkv + hk) * D + d] = val;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+
+bool tma_eligible(int D, int dtype, int block_size, bool paged, const int64_t* st, const void* k, const void* v) {
+    if (dtype != PLI_BF16 && dtype != PLI_F16) return false;
+    if (D != 64 && D != 128) return false;
+    if (paged && (!is_pow2(block_size) || block_size < 8 || block_size > 256)) return false;
+    if ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) return false;
+    // every non-unit stride must be a multiple of 16 bytes (8 elements) for the tensor map
+    for (int i = 0; i < 4; ++i)
+        if (st[i] % 8 != 0) return false;
+    if (st[2] <= 0 || st[3] <= 0 || st[0] <= 0) return false;
+    return true;
+}
+
+int make_kv_map(CUtensorMap* map, const void* base, int dtype, int D, int Hkv, bool paged, int block_size,
+                int num_layers_hint, int64_t extent, int max_seq_len, const int64_t* st, int box_tokens) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (enc == nullptr) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const CUtensorMapDataType dt = dtype == PLI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    // dims (fastest first): d, head, slot/token, X (layer | 1), Y (page | batch)
+    cuuint64_t dims[5] = {(cuuint64_t)D, (cuuint64_t)Hkv, (cuuint64_t)(paged ? block_size : max_seq_len),
+                          (cuuint64_t)(paged ? num_layers_hint : 1), (cuuint64_t)extent};
+    const int64_t x_stride = paged ? st[1] : st[0];
+    cuuint64_t strides[4] = {(cuuint64_t)st[3] * 2, (cuuint64_t)st[2] * 2, (cuuint64_t)(x_stride > 0 ? x_stride : st[0]) * 2,
+                             (cuuint64_t)st[0] * 2};
+    cuuint32_t box[5] = {64, 1, (cuuint32_t)box_tokens, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled(KV) failed with CUresult %d", (int)r);
+    return PLI_OK;
+}
+
+template <int kD, bool kBf16, bool kRows16>
+int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaParams& p, dim3 grid, cudaStream_t stream) {
+    auto kern = decode_tma_kernel<kD, kBf16, kRows16>;
+    constexpr int kTileBytes = (kD / 64) * kStageTokens * 128;
+    const size_t merge_bytes = (size_t)(128 + 64 * kD) * sizeof(float);
+    size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 1024;
+    if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
+    PLI_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}
+
+}  // namespace
+}  // namespace pli
+
+using namespace pli;
+
+extern "C" int pli_decode_num_splits(int B, int Hkv, int max_seq_len) {
+    if (B <= 0 || Hkv <= 0 || max_seq_len <= 0) return 1;
+    // Aim for ~4 waves of (2 CTAs x SMs) with at least 256 tokens per split.
+    const int64_t units = (int64_t)B * Hkv;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int64_t target = (int64_t)sms * 2 * 4;
+    int by_fill = (int)((target + units - 1) / units);
+    int by_len = (max_seq_len + 255) / 256;
+    int s = by_fill < by_len ? by_fill : by_len;
+    if (s < 1) s = 1;
+    if (s > 64) s = 64;
+    return s;
+}
+
+extern "C" size_t pli_decode_workspace_bytes(int B, int Hq, int D, int num_splits) {
+    if (B <= 0 || Hq <= 0 || D <= 0 || num_splits <= 0) return 0;
+    return (size_t)B * Hq * num_splits * (size_t)(D + 1) * sizeof(float);
+}
+
+extern "C" int pli_decode_kernel_kind(int D, int dtype, int block_size, const int64_t kv_strides[4], const void* k_store,
+                                      const void* v_store) {
+    return tma_eligible(D, dtype, block_size, block_size > 0, kv_strides, k_store, v_store) ? PLI_KIND_MMA_TMA
+                                                                                          : PLI_KIND_SIMT;
+}
+
+static int check_decode_args(const void* q, const void* k, const void* v, const int32_t* seq_lens, int B, int Hq, int Hkv,
+                             int D, int max_seq_len, int block_size, bool paged, int num_splits) {
+    if (!q || !k || !v || !seq_lens) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || D <= 0) return set_error(PLI_ERR_INVALID, "non-positive dimension");
+    if (Hq % Hkv != 0) return set_error(PLI_ERR_INVALID, "Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
+    if (D > 256) return set_error(PLI_ERR_UNSUPPORTED, "head_dim %d > 256", D);
+    if (max_seq_len <= 0) return set_error(PLI_ERR_INVALID, "max_seq_len must be positive");
+    if (paged && block_size <= 0) return set_error(PLI_ERR_INVALID, "block_size must be positive for paged KV");
+    if (num_splits <= 0) return set_error(PLI_ERR_INVALID, "num_splits must be positive");
+    if (B > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B > 65535");
+    return PLI_OK;
+}
+
+extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                                  const int32_t* seq_lens, int B, int Hq, int Hkv, int D, int max_seq_len, int block_size,
+                                  int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
+                                  const int64_t kv_strides[4], float scale, int dtype, int num_splits, void* workspace,
+                                  size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const bool paged = block_table != nullptr;
+    if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
+    int rc = check_decode_args(q, k_store, v_store, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, paged, num_splits);
+    if (rc) return rc;
+    if (workspace == nullptr || workspace_bytes < pli_decode_workspace_bytes(B, Hq, D, num_splits))
+        return set_error(PLI_ERR_INVALID, "workspace too small: need %zu bytes",
+                         pli_decode_workspace_bytes(B, Hq, D, num_splits));
+    float* o_part = static_cast<float*>(workspace);
+    float* lse_part = o_part + (size_t)B * Hq * num_splits * D;
+    const int G = Hq / Hkv;
+
+    if (scale > 0.f && tma_eligible(D, dtype, block_size, paged, kv_strides, k_store, v_store) && (q_strides[0] % 2 == 0) &&
+        (q_strides[1] % 2 == 0) && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+        const int box_tokens = paged ? (block_size < kStageTokens ? block_size : kStageTokens) : kStageTokens;
+        // layers extent: the layer coordinate must be inside the tensor; layer+1 is a safe lower bound
+        CUtensorMap mk, mv;
+        rc = make_kv_map(&mk, k_store, dtype, D, Hkv, paged, block_size, layer + 1, kv_extent, max_seq_len, kv_strides,
+                         box_tokens);
+        if (rc) return rc;
+        rc = make_kv_map(&mv, v_store, dtype, D, Hkv, paged, block_size, layer + 1, kv_extent, max_seq_len, kv_strides,
+                         box_tokens);
+        if (rc) return rc;
+        DecodeTmaParams p;
+        p.q = q;
+        p.table = block_table;
+        p.seq_lens = seq_lens;
+        p.o_part = o_part;
+        p.lse_part = lse_part;
+        p.qsb = q_strides[0];
+        p.qsh = q_strides[1];
+        p.Hq = Hq;
+        p.Hkv = Hkv;
+        p.G = G;
+        p.bs = paged ? block_size : 1;
+        p.table_stride = table_stride;
+        p.layer = layer;
+        p.S = num_splits;
+        p.box_tokens = box_tokens;
+        p.scale_log2 = scale * kLog2e;
+        const int hchunks = (G + 15) / 16;
+        dim3 grid(num_splits, Hkv * hchunks, B);
+        const bool rows16 = G > 8;
+        const bool bf16 = dtype == PLI_BF16;
+#define PLI_GO(DD, BF, R16) return launch_tma_t<DD, BF, R16>(mk, mv, p, grid, stream)
+        if (D == 128) {
+            if (bf16) { if (rows16) PLI_GO(128, true, true); else PLI_GO(128, true, false); }
+            else      { if (rows16) PLI_GO(128, false, true); else PLI_GO(128, false, false); }
+        } else {
+            if (bf16) { if (rows16) PLI_GO(64, true, true); else PLI_GO(64, true, false); }
+            else      { if (rows16) PLI_GO(64, false, true); else PLI_GO(64, false, false); }
+        }
+#undef PLI_GO
+    }
+
+    // generic SIMT path
+    if (Hq > 65535) return set_error(PLI_ERR_UNSUPPORTED, "Hq > 65535");
+    const int dc = (D + 31) / 32;
+    dim3 grid(num_splits, Hq, B);
+    const size_t smem = (size_t)4 * D * sizeof(float);
+    const int bs = paged ? block_size : 1;
+#define PLI_SIMT(T, N)                                                                                              \
+    decode_simt_kernel<T, N><<<grid, 128, smem, stream>>>(                                                          \
+        (const T*)q, (const T*)k_store, (const T*)v_store, block_table, seq_lens, Hq, Hkv, D, bs, table_stride,     \
+        layer, q_strides[0], q_strides[1], kv_strides[0], kv_strides[1], kv_strides[2], kv_strides[3], scale,       \
+        num_splits, o_part, lse_part)
+#define PLI_SIMT_D(T)                   \
+    if (dc <= 1) PLI_SIMT(T, 1);        \
+    else if (dc <= 2) PLI_SIMT(T, 2);   \
+    else if (dc <= 4) PLI_SIMT(T, 4);   \
+    else PLI_SIMT(T, 8)
+    if (dtype == PLI_F32) { PLI_SIMT_D(float); }
+    else if (dtype == PLI_BF16) { PLI_SIMT_D(__nv_bfloat16); }
+    else if (dtype == PLI_F16) { PLI_SIMT_D(__half); }
+    else return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
+#undef PLI_SIMT_D
+#undef PLI_SIMT
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}
+
+extern "C" int pli_decode_combine(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
+                                  const int64_t o_strides[2], int dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!workspace || !o) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (B <= 0 || Hq <= 0 || D <= 0 || num_splits <= 0) return set_error(PLI_ERR_INVALID, "non-positive dimension");
+    if (B > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B > 65535");
+    const float* o_part = static_cast<const float*>(workspace);
+    const float* lse_part = o_part + (size_t)B * Hq * num_splits * D;
+    dim3 grid(Hq, B);
+    const int threads = D >= 128 ? 128 : (D >= 64 ? 64 : 32);
+    if (dtype == PLI_F32)
+        decode_combine_kernel<float><<<grid, threads, 0, stream>>>(o_part, lse_part, (float*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1]);
+    else if (dtype == PLI_BF16)
+        decode_combine_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(o_part, lse_part, (__nv_bfloat16*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1]);
+    else if (dtype == PLI_F16)
+        decode_combine_kernel<__half><<<grid, threads, 0, stream>>>(o_part, lse_part, (__half*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1]);
+    else
+        return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}
+
+extern "C" int pli_decode_fwd(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                              const int32_t* seq_lens, void* o, float* lse, int B, int Hq, int Hkv, int D, int max_seq_len,
+                              int block_size, int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
+                              const int64_t kv_strides[4], const int64_t o_strides[2], float scale, int dtype,
+                              int num_splits, void* workspace, size_t workspace_bytes, void* stream) {
+    if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
+    int rc = pli_decode_splitkv(q, k_store, v_store, block_table, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size,
+                                table_stride, layer, kv_extent, q_strides, kv_strides, scale, dtype, num_splits, workspace,
+                                workspace_bytes, stream);
+    if (rc) return rc;
+    return pli_decode_combine(workspace, o, lse, B, Hq, D, num_splits, o_strides, dtype, stream);
+}
+
+extern "C" int pli_kv_append(const void* k_new, const void* v_new, void* k_store, void* v_store, const int32_t* block_table,
+                             const int32_t* start_pos, int B, int n_new, int Hkv, int D, int block_size, int table_stride,
+                             int layer, const int64_t new_strides[3], const int64_t kv_strides[4], int dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!k_new || !v_new || !k_store || !v_store || !start_pos) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (B <= 0 || Hkv <= 0 || D <= 0 || n_new < 0) return set_error(PLI_ERR_INVALID, "bad dimension");
+    if (n_new == 0) return PLI_OK;
+    if (B > 65535 || n_new > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B and n_new must be <= 65535");
+    const bool paged = block_table != nullptr;
+    if (paged && block_size <= 0) return set_error(PLI_ERR_INVALID, "block_size must be positive for paged KV");
+    const int esz = dtype == PLI_F32 ? 4 : 2;
+    int vec = 16 / esz;
+    auto aligned = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    bool ok = D % vec == 0 && aligned(k_new) && aligned(v_new) && aligned(k_store) && aligned(v_store);
+    for (int i = 0; i < 3; ++i) ok = ok && new_strides[i] % vec == 0;
+    for (int i = 0; i < 4; ++i) ok = ok && kv_strides[i] % vec == 0;
+    if (!ok) vec = 1;
+    const int per_tok = Hkv * (D / vec);
+    dim3 grid((per_tok + 127) / 128, n_new, B);
+    const int bs = paged ? block_size : 1;
+#define PLI_APPEND(T)                                                                                                 \
+    kv_append_kernel<T><<<grid, 128, 0, stream>>>((const T*)k_new, (const T*)v_new, (T*)k_store, (T*)v_store,         \
+                                                  block_table, start_pos, n_new, Hkv, D, bs, table_stride, layer,     \
+                                                  new_strides[0], new_strides[1], new_strides[2], kv_strides[0],      \
+                                                  kv_strides[1], kv_strides[2], kv_strides[3], vec)
+    if (dtype == PLI_F32) PLI_APPEND(float);
+    else if (dtype == PLI_BF16) PLI_APPEND(__nv_bfloat16);
+    else if (dtype == PLI_F16) PLI_APPEND(__half);
+    else return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
+#undef PLI_APPEND
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}
+
+extern "C" int pli_paged_gather(const void* store, void* out, const int32_t* block_table, const int32_t* seq_lens, int B,
+                                int max_len, int Hkv, int D, int block_size, int table_stride, int layer,
+                                const int64_t kv_strides[4], int dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!store || !out || !seq_lens) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (B <= 0 || max_len <= 0 || Hkv <= 0 || D <= 0) return set_error(PLI_ERR_INVALID, "non-positive dimension");
+    if (B > 65535 || max_len > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B and max_len must be <= 65535");
+    const bool paged = block_table != nullptr;
+    if (paged && block_size <= 0) return set_error(PLI_ERR_INVALID, "block_size must be positive for paged KV");
+    dim3 grid((Hkv * D + 255) / 256, max_len, B);
+    const int bs = paged ? block_size : 1;
+#define PLI_GATHER(T)                                                                                              \
+    paged_gather_kernel<T><<<grid, 256, 0, stream>>>((const T*)store, (T*)out, block_table, seq_lens, max_len, Hkv, D, bs, \
+                                                     table_stride, layer, kv_strides[0], kv_strides[1], kv_strides[2],  \
+                                                     kv_strides[3])
+    if (dtype == PLI_F32) PLI_GATHER(float);
+    else if (dtype == PLI_BF16) PLI_GATHER(__nv_bfloat16);
+    else if (dtype == PLI_F16) PLI_GATHER(__half);
+    else return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
+#undef PLI_GATHER
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}

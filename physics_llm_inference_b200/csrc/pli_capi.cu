@@ -1,0 +1,117 @@
+// pli_capi.cu — C-ABI entry points (include/pli_attention.h): argument validation, kernel
+// selection, error text.  Kernels live in prefill_tcgen05.cu, prefill_simt.cu and decode.cu.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace pli {
+
+static thread_local char g_err[512] = "";
+static thread_local uint64_t g_launches = 0;
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches += (uint64_t)n; }
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+int sm_count() {
+    static thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+        cached = prop.multiProcessorCount;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+static int device_is_sm100() {
+    static thread_local int cached_dev = -1, major = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev != cached_dev) {
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+        cached_dev = dev;
+    }
+    return major == 10;
+}
+
+static bool tcgen05_eligible(int D, int dtype, const int64_t* qs, const int64_t* ks, const int64_t* vs,
+                             const int64_t* os, const void* q, const void* k, const void* v, const void* o) {
+    if (dtype != PLI_BF16 && dtype != PLI_F16) return false;
+    if (D != 64 && D != 128) return false;
+    const uintptr_t ptrs = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                           reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o);
+    if (ptrs & 15) return false;
+    for (int i = 0; i < 3; ++i) {
+        if (qs[i] % 8 || ks[i] % 8 || vs[i] % 8 || os[i] % 8) return false;
+        if (qs[i] < 0 || ks[i] < 0 || vs[i] < 0 || os[i] < 0) return false;
+    }
+    // token strides must be real (TMA cannot broadcast a zero stride)
+    if (qs[2] == 0 || ks[2] == 0 || vs[2] == 0 || os[2] == 0) return false;
+    return true;
+}
+
+}  // namespace pli
+
+using namespace pli;
+
+extern "C" int pli_abi_version(void) { return PLI_ABI_VERSION; }
+extern "C" const char* pli_last_error(void) { return g_err; }
+extern "C" int pli_set_device(int device) {
+    PLI_CUDA_CHECK(cudaSetDevice(device));
+    if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "CUDA device %d is not sm_100 (B200)", device);
+    return PLI_OK;
+}
+extern "C" uint64_t pli_launch_count(void) { return g_launches; }
+extern "C" void pli_reset_launch_count(void) { g_launches = 0; }
+
+extern "C" int pli_prefill_kernel_kind(int D, int dtype, const int64_t q_strides[3], const int64_t k_strides[3],
+                                       const int64_t v_strides[3], const int64_t o_strides[3], const void* q,
+                                       const void* k, const void* v, const void* o) {
+    if (dtype != PLI_BF16 && dtype != PLI_F16 && dtype != PLI_F32) return PLI_KIND_NONE;
+    if (D < 1 || D > 256) return PLI_KIND_NONE;
+    return tcgen05_eligible(D, dtype, q_strides, k_strides, v_strides, o_strides, q, k, v, o) ? PLI_KIND_TCGEN05
+                                                                                              : PLI_KIND_SIMT;
+}
+
+extern "C" int pli_prefill_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv,
+                               int Nq, int Nk, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                               const int64_t v_strides[3], const int64_t o_strides[3], float scale, int causal,
+                               int dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!q || !k || !v || !o) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (!q_strides || !k_strides || !v_strides || !o_strides) return set_error(PLI_ERR_INVALID, "null stride array");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || D <= 0)
+        return set_error(PLI_ERR_INVALID, "non-positive dimension (B=%d Hq=%d Hkv=%d Nq=%d Nk=%d D=%d)", B, Hq, Hkv, Nq, Nk, D);
+    if (Hq % Hkv != 0) return set_error(PLI_ERR_INVALID, "Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
+    if (causal && Nq > Nk)
+        return set_error(PLI_ERR_INVALID, "causal attention needs Nq <= Nk (got %d > %d): rows without a visible key", Nq, Nk);
+    if (dtype != PLI_BF16 && dtype != PLI_F16 && dtype != PLI_F32) return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
+    if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "current CUDA device is not sm_100 (B200)");
+    if (scale > 0.f && tcgen05_eligible(D, dtype, q_strides, k_strides, v_strides, o_strides, q, k, v, o))
+        return launch_prefill_tcgen05(q, k, v, o, lse, B, Hq, Hkv, Nq, Nk, D, q_strides, k_strides, v_strides, o_strides,
+                                      scale, causal, dtype, stream);
+    return launch_prefill_simt(q, k, v, o, lse, B, Hq, Hkv, Nq, Nk, D, q_strides, k_strides, v_strides, o_strides, scale,
+                               causal, dtype, stream);
+}

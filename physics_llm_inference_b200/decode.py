@@ -1,0 +1,200 @@
+"""Decode-time attention over the ch02 contiguous cache or the ch07 paged pools.
+
+The reference computes this inside `CachedGQA.forward` (ch02/cached_generation.py:72-94: slice the
+cache to seq_len, transpose, repeat_interleave K/V G times, QK^T/sqrt(D), no mask when one new
+token, softmax, PV).  `flash_decode` is that attention block for one query token per sequence as a
+split-KV kernel + log-sum-exp combine, reading K/V in place:
+
+  contiguous  k_cache, v_cache (B, max_seq_len, Hkv, D)            ch02/kv_cache.py:25-34
+  paged       k_cache, v_cache (P, num_layers, bs, Hkv, D) pools   ch07/paged_memory.py:38-48
+              + block_tables (B, max_pages) int32: token t of sequence b is at
+                page block_tables[b, t // bs], slot t % bs          ch07/paged_memory.py:54,84-86
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .kv_cache import KVCache, LayerKVCache
+from .paged_memory import PagedKVCache
+
+
+def decode_num_splits(B: int, Hkv: int, max_seq_len: int) -> int:
+    return int(_lib.load().pli_decode_num_splits(B, Hkv, max_seq_len))
+
+
+def decode_workspace(B: int, Hq: int, D: int, num_splits: int, device) -> torch.Tensor:
+    nbytes = int(_lib.load().pli_decode_workspace_bytes(B, Hq, D, num_splits))
+    return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+
+def flash_decode(
+    q: torch.Tensor,
+    k_cache: torch.Tensor,
+    v_cache: torch.Tensor,
+    seq_lens,
+    *,
+    block_tables: torch.Tensor | None = None,
+    layer: int = 0,
+    scale: float | None = None,
+    return_lse: bool = False,
+    num_splits: int | None = None,
+    max_seq_len: int | None = None,
+    workspace: torch.Tensor | None = None,
+    out: torch.Tensor | None = None,
+):
+    """Attention of one query token per sequence over cached K/V.
+
+    q         (B, Hq, 1, D) or (B, Hq, D)
+    seq_lens  int (one length for the whole batch, like the reference's caches) or (B,) int32 CUDA
+              tensor (ragged batch; no host sync is made to read it)
+    max_seq_len  host upper bound of seq_lens, used to pick the split count; defaults to the int
+              seq_lens, else the cache length (contiguous) / table width * page size (paged)
+    Returns o shaped like q (and lse (B, Hq) float32 when return_lse).
+    """
+    if not (q.is_cuda and k_cache.is_cuda and v_cache.is_cuda):
+        raise RuntimeError("flash_decode runs on CUDA tensors only: there is no CPU fallback for the decode path")
+    if q.dim() == 4:
+        if q.shape[2] != 1:
+            raise RuntimeError(f"decode takes one query token per sequence; got q {tuple(q.shape)} "
+                               "(use flash_attention_forward(..., causal=True) for chunks)")
+        q3 = q[:, :, 0, :]
+    elif q.dim() == 3:
+        q3 = q
+    else:
+        raise RuntimeError(f"q must be (B, Hq, 1, D) or (B, Hq, D); got {tuple(q.shape)}")
+    if q3.stride(-1) != 1:
+        q3 = q3.contiguous()
+    B, Hq, D = q3.shape
+    if not (q.dtype == k_cache.dtype == v_cache.dtype):
+        raise RuntimeError(f"q and the KV storage must share a dtype; got {q.dtype}, {k_cache.dtype}, {v_cache.dtype}")
+    if k_cache.shape != v_cache.shape or k_cache.stride() != v_cache.stride():
+        raise RuntimeError("k and v storage must have the same shape and strides")
+    if k_cache.stride(-1) != 1:
+        raise RuntimeError("KV storage must have a unit head_dim stride")
+    dev = q.device
+    paged = block_tables is not None
+    if paged:
+        if k_cache.dim() != 5:
+            raise RuntimeError(f"paged pools must be (P, layers, bs, Hkv, D); got {tuple(k_cache.shape)}")
+        P, n_layers, bs, Hkv, Dk = k_cache.shape
+        if not 0 <= layer < n_layers:
+            raise IndexError(f"layer {layer} out of range for {n_layers} layers")
+        if block_tables.dtype != torch.int32 or not block_tables.is_cuda or block_tables.dim() != 2:
+            raise RuntimeError("block_tables must be a 2-D CUDA int32 tensor")
+        if block_tables.shape[0] != B:
+            raise RuntimeError(f"block_tables has {block_tables.shape[0]} rows for batch {B}")
+        if block_tables.stride(-1) != 1:
+            block_tables = block_tables.contiguous()
+        kv_strides = k_cache.stride()[:4]
+        kv_extent, cap = P, block_tables.shape[1] * bs
+        table_ptr, tstride = block_tables.data_ptr(), block_tables.stride(0)
+    else:
+        if k_cache.dim() != 4:
+            raise RuntimeError(f"contiguous cache must be (B, max_seq_len, Hkv, D); got {tuple(k_cache.shape)}")
+        Bk, cap, Hkv, Dk = k_cache.shape
+        if Bk != B:
+            raise RuntimeError(f"cache batch {Bk} does not match q batch {B}")
+        bs = 0
+        kv_strides = (k_cache.stride(0), 0, k_cache.stride(1), k_cache.stride(2))
+        kv_extent = B
+        table_ptr, tstride = None, 0
+    if Dk != D:
+        raise RuntimeError(f"head_dim mismatch: q {D}, cache {Dk}")
+    if Hq % Hkv != 0:
+        raise RuntimeError(f"num_heads ({Hq}) must be a multiple of num_kv_heads ({Hkv})")
+
+    if isinstance(seq_lens, int):
+        if not 0 < seq_lens <= cap:
+            raise ValueError(f"seq_len {seq_lens} outside (0, {cap}]")
+        lens = torch.full((B,), seq_lens, dtype=torch.int32, device=dev)
+        if max_seq_len is None:
+            max_seq_len = seq_lens
+    else:
+        lens = seq_lens
+        if lens.dtype != torch.int32 or not lens.is_cuda or lens.shape != (B,):
+            raise RuntimeError("seq_lens must be an int or a (B,) CUDA int32 tensor")
+        if not lens.is_contiguous():
+            lens = lens.contiguous()
+        if max_seq_len is None:
+            max_seq_len = cap
+    max_seq_len = min(int(max_seq_len), cap)
+    if scale is None:
+        scale = D ** -0.5
+
+    lib = _lib.load()
+    if num_splits is None:
+        num_splits = int(lib.pli_decode_num_splits(B, Hkv, max_seq_len))
+    need = int(lib.pli_decode_workspace_bytes(B, Hq, D, num_splits))
+    if workspace is None:
+        workspace = torch.empty(need // 4, dtype=torch.float32, device=dev)
+    elif workspace.numel() * workspace.element_size() < need or not workspace.is_cuda:
+        raise RuntimeError(f"workspace too small: need {need} bytes")
+    if out is None:
+        out = torch.empty((B, Hq, D), dtype=q.dtype, device=dev)
+    elif out.shape != (B, Hq, D) or out.dtype != q.dtype or out.stride(-1) != 1:
+        raise RuntimeError("out must be (B, Hq, D), q's dtype, unit inner stride")
+    lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
+
+    with torch.cuda.device(dev):
+        _lib.check(lib.pli_set_device(dev.index))
+        rc = lib.pli_decode_fwd(
+            q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(), out.data_ptr(),
+            lse.data_ptr() if lse is not None else None, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
+            _lib.i64(q3.stride(0), q3.stride(1)), _lib.i64(*kv_strides), _lib.i64(out.stride(0), out.stride(1)),
+            float(scale), _lib.dtype_code(q.dtype), num_splits, workspace.data_ptr(),
+            workspace.numel() * workspace.element_size(), _lib.current_stream_ptr(dev))
+    _lib.check(rc)
+    o = out.unsqueeze(2) if q.dim() == 4 else out
+    return (o, lse) if return_lse else o
+
+
+def decode_kernel_kind(k_cache: torch.Tensor, block_tables=None) -> str:
+    """'mma_tma' or 'simt': which split-KV kernel serves this storage."""
+    if block_tables is not None:
+        bs, st = k_cache.shape[2], k_cache.stride()[:4]
+    else:
+        bs, st = 0, (k_cache.stride(0), 0, k_cache.stride(1), k_cache.stride(2))
+    kind = _lib.load().pli_decode_kernel_kind(k_cache.shape[-1], _lib.dtype_code(k_cache.dtype), bs, _lib.i64(*st),
+                                              k_cache.data_ptr(), k_cache.data_ptr())
+    return _lib.KIND_NAMES[kind]
+
+
+def decode_with_cache(q: torch.Tensor, cache, **kw):
+    """flash_decode over a reference-style `KVCache` (ch02/kv_cache.py) or `LayerKVCache`
+    (ch02/cached_generation.py) object: attends to the first cache.seq_len tokens."""
+    if isinstance(cache, KVCache) or hasattr(cache, "k_cache"):
+        k, v = cache.k_cache, cache.v_cache
+    elif isinstance(cache, LayerKVCache) or hasattr(cache, "k"):
+        k, v = cache.k, cache.v
+    else:
+        raise TypeError(f"unsupported cache object {type(cache)}")
+    return flash_decode(q, k, v, int(cache.seq_len), **kw)
+
+
+def decode_with_paged(q: torch.Tensor, paged: PagedKVCache, request_ids, *, layer: int = 0, **kw):
+    """flash_decode over a `PagedKVCache` (ch07/paged_memory.py) for the given request ids."""
+    if paged.k_cache is None:
+        raise RuntimeError("PagedKVCache has no device pools (constructed without CUDA)")
+    bt, lens = paged.block_table_tensor(request_ids, device=q.device)
+    max_len = max(paged.block_tables[r].num_tokens for r in request_ids)
+    return flash_decode(q, paged.k_cache, paged.v_cache, lens, block_tables=bt, layer=layer, max_seq_len=max_len, **kw)
+
+
+def paged_gather(store: torch.Tensor, block_tables: torch.Tensor, seq_lens: torch.Tensor, max_len: int,
+                 layer: int = 0) -> torch.Tensor:
+    """Gather one layer of a paged pool to (B, max_len, Hkv, D) with the kernels' address rule
+    (parity aid: lets tests assert page indexing bit-exactly; rows >= seq_len are zero)."""
+    if store.dim() != 5 or not store.is_cuda:
+        raise RuntimeError("store must be a CUDA pool (P, layers, bs, Hkv, D)")
+    B = block_tables.shape[0]
+    _, _, bs, Hkv, D = store.shape
+    out = torch.empty((B, max_len, Hkv, D), dtype=store.dtype, device=store.device)
+    lib = _lib.load()
+    with torch.cuda.device(store.device):
+        _lib.check(lib.pli_set_device(store.device.index))
+        rc = lib.pli_paged_gather(store.data_ptr(), out.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(), B,
+                                  max_len, Hkv, D, bs, block_tables.stride(0), layer, _lib.i64(*store.stride()[:4]),
+                                  _lib.dtype_code(store.dtype), _lib.current_stream_ptr(store.device))
+    _lib.check(rc)
+    return out

@@ -1,0 +1,149 @@
+"""Drop-in for the reference's `ch06.flash_attention_forward` on B200.
+
+Keeps the reference signature and layouts (ch06/flash_attention.py:14-20: `q, k, v` of shape
+(B, H, N, D), `scale=None` -> D**-0.5, `config=None`, returns a tensor shaped and typed like q)
+and adds, keyword-only, what BASELINE.json's north_star asks for on top of ch06:
+
+  causal=False      ch01/gqa.py:33-34 / ch02/cached_generation.py:85-91 mask (bottom-right aligned
+                    when Nq < Nk); the default stays non-causal like the reference.
+  return_lse=False  also return log-sum-exp (B, Hq, Nq) float32 (ch06 computes row_max/row_sum at
+                    :71-72 and drops them).
+  k, v may have Hkv heads with Hq % Hkv == 0: q-head h reads kv-head h // (Hq // Hkv)
+                    (ch01/gqa.py:14,30-31) without materialising the repeat_interleave copy.
+
+All arithmetic runs in the CUDA library behind include/pli_attention.h; there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+
+
+@dataclass
+class FlashAttentionConfig:
+    """Tile hints of ch06/flash_attention.py:6-11.  The sm_100a kernels use fixed 128x128 tiles, so
+    the values are accepted for compatibility and do not change the result (in the reference they
+    do not change it either: any block_q/block_k computes the same function)."""
+    block_q: int = 64
+    block_k: int = 64
+    num_warps: int = 4
+    num_stages: int = 2
+
+
+def _unit_inner(x: torch.Tensor) -> torch.Tensor:
+    return x if x.stride(-1) == 1 else x.contiguous()
+
+
+def _check_inputs(q, k, v):
+    for name, x in (("q", q), ("k", k), ("v", v)):
+        if not isinstance(x, torch.Tensor):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if x.dim() != 4:
+            raise RuntimeError(f"{name} must have shape (B, H, N, D); got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError(
+                f"{name} is on {x.device}: this is the B200 CUDA path of flash_attention_forward and has no "
+                "CPU fallback (the CPU restatement lives in oracle/ and is test infrastructure only)")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise RuntimeError(f"q, k, v must share a dtype; got {q.dtype}, {k.dtype}, {v.dtype}")
+    if not (q.device == k.device == v.device):
+        raise RuntimeError("q, k, v must be on the same device")
+    B, Hq, Nq, D = q.shape
+    if k.shape != v.shape:
+        raise RuntimeError(f"k and v must have the same shape; got {tuple(k.shape)} and {tuple(v.shape)}")
+    if k.shape[0] != B or k.shape[3] != D:
+        raise RuntimeError(f"k/v shape {tuple(k.shape)} does not match q shape {tuple(q.shape)} in batch or head_dim")
+    if Hq % k.shape[1] != 0:
+        raise RuntimeError(f"num_heads ({Hq}) must be a multiple of num_kv_heads ({k.shape[1]})")
+    if min(B, Hq, Nq, D, k.shape[2]) <= 0:
+        raise RuntimeError(f"empty attention problem: q {tuple(q.shape)}, k {tuple(k.shape)}")
+
+
+def flash_attention_forward(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    scale: float | None = None,
+    config: FlashAttentionConfig | None = None,
+    *,
+    causal: bool = False,
+    return_lse: bool = False,
+):
+    """softmax(Q K^T * scale [+ causal mask]) V on the GPU; see the module docstring."""
+    if config is None:
+        config = FlashAttentionConfig()
+    _check_inputs(q, k, v)
+    B, Hq, Nq, D = q.shape
+    Hkv, Nk = k.shape[1], k.shape[2]
+    if causal and Nq > Nk:
+        raise ValueError(f"causal attention needs Nq <= Nk (got Nq={Nq}, Nk={Nk})")
+    if scale is None:
+        scale = D ** -0.5
+    q, k, v = _unit_inner(q), _unit_inner(k), _unit_inner(v)
+    out = torch.empty_like(q)
+    if out.stride(-1) != 1:
+        out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, Hq, Nq), dtype=torch.float32, device=q.device) if return_lse else None
+
+    lib = _lib.load()
+    with torch.cuda.device(q.device):
+        _lib.check(lib.pli_set_device(q.device.index))
+        rc = lib.pli_prefill_fwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None,
+            B, Hq, Hkv, Nq, Nk, D,
+            _lib.i64(*q.stride()[:3]), _lib.i64(*k.stride()[:3]), _lib.i64(*v.stride()[:3]), _lib.i64(*out.stride()[:3]),
+            float(scale), int(bool(causal)), _lib.dtype_code(q.dtype), _lib.current_stream_ptr(q.device))
+    _lib.check(rc)
+    return (out, lse) if return_lse else out
+
+
+# the name BASELINE.json's north_star uses
+flash_attention = flash_attention_forward
+
+
+def prefill_kernel_kind(q, k, v) -> str:
+    """'tcgen05' or 'simt': which kernel family `flash_attention_forward` uses for these tensors."""
+    _check_inputs(q, k, v)
+    q, k, v = _unit_inner(q), _unit_inner(k), _unit_inner(v)
+    out = torch.empty_like(q)
+    kind = _lib.load().pli_prefill_kernel_kind(
+        q.shape[3], _lib.dtype_code(q.dtype), _lib.i64(*q.stride()[:3]), _lib.i64(*k.stride()[:3]),
+        _lib.i64(*v.stride()[:3]), _lib.i64(*out.stride()[:3]), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+        out.data_ptr())
+    return _lib.KIND_NAMES[kind]
+
+
+# ---- accounting conventions of ch06/attention_memory.py:64-76 and ch06/flash_attention.py:77-104 ----
+def attention_flops(batch_size: int, num_heads: int, seq_len: int, head_dim: int) -> int:
+    """2BHN^2D (QK^T) + 5BHN^2 (softmax) + 2BHN^2D (PV), as ch06/attention_memory.py:64-76."""
+    qk = 2 * batch_size * num_heads * seq_len * seq_len * head_dim
+    return qk + 5 * batch_size * num_heads * seq_len * seq_len + qk
+
+
+def flash_attention_memory_bytes(batch_size: int, num_heads: int, seq_len: int, head_dim: int,
+                                 block_size: int = 64, dtype_bytes: int = 2) -> dict:
+    """HBM traffic of the tiled algorithm: Q, K, V, O once each (ch06/flash_attention.py:77-104)."""
+    qkv = 3 * batch_size * num_heads * seq_len * head_dim * dtype_bytes
+    out = batch_size * num_heads * seq_len * head_dim * dtype_bytes
+    tile = block_size * head_dim * dtype_bytes
+    sram = 4 * tile + block_size * block_size * dtype_bytes + block_size * 2 * dtype_bytes
+    naive = qkv + out + batch_size * num_heads * seq_len * seq_len * dtype_bytes
+    return {
+        "hbm_bytes": qkv + out,
+        "hbm_mb": (qkv + out) / 1024 / 1024,
+        "sram_bytes_per_block": sram,
+        "sram_kb_per_block": sram / 1024,
+        "naive_hbm_bytes": naive,
+        "memory_savings": f"{seq_len // block_size}x",
+    }
+
+
+def prefill_algorithmic_flops(B: int, Hq: int, Nq: int, Nk: int, D: int, causal: bool) -> float:
+    """Roofline numerator: 4*B*Hq*Nq*Nk*D, x 1/2 for the causal square
+    (FlashAttention-paper convention); a rectangular causal problem counts its full Nq x (Nk-Nq)
+    block plus half of the Nq x Nq triangle."""
+    pairs = Nq * Nk if not causal else Nq * (Nk - Nq) + Nq * Nq / 2
+    return 4.0 * B * Hq * D * pairs

@@ -1,0 +1,118 @@
+"""Multi-GPU launcher pieces: shard attention over KV-head groups, gather only on request.
+
+The reference has no distributed code (ch09's tensor parallelism is shape-only and
+`nccl_primitives.py` is a cost model).  Attention needs no exchange step: every (batch, KV-head
+group) is independent because softmax never crosses heads or batch and a KV head is shared only
+by its own G = Hq/Hkv query heads (ch01/gqa.py:14,30-31).  So each rank (one process per GPU) owns
+a contiguous slice of KV heads with their query heads — what a tensor-parallel server holds
+anyway — and runs the single-GPU kernels on it.  NCCL is used only by `gather_heads`, when the
+caller wants the full (B, Hq, N, D) output on every rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+
+@dataclass(frozen=True)
+class HeadShard:
+    """Which heads (and, if there are more ranks than KV heads, which batch rows) a rank owns."""
+    rank: int
+    world_size: int
+    num_heads: int
+    num_kv_heads: int
+    batch: int
+    kv_start: int
+    kv_end: int
+    b_start: int
+    b_end: int
+
+    @property
+    def group_size(self) -> int:
+        return self.num_heads // self.num_kv_heads
+
+    @property
+    def q_start(self) -> int:
+        return self.kv_start * self.group_size
+
+    @property
+    def q_end(self) -> int:
+        return self.kv_end * self.group_size
+
+    @property
+    def units(self) -> int:
+        """(batch, KV-head group) units on this rank."""
+        return (self.kv_end - self.kv_start) * (self.b_end - self.b_start)
+
+
+def make_shard(rank: int, world_size: int, num_heads: int, num_kv_heads: int, batch: int) -> HeadShard:
+    if num_heads % num_kv_heads != 0:
+        raise ValueError(f"num_heads ({num_heads}) must be a multiple of num_kv_heads ({num_kv_heads})")
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    if num_kv_heads % world_size == 0:
+        per = num_kv_heads // world_size
+        return HeadShard(rank, world_size, num_heads, num_kv_heads, batch, rank * per, (rank + 1) * per, 0, batch)
+    if world_size % num_kv_heads == 0 and batch % (world_size // num_kv_heads) == 0:
+        ways = world_size // num_kv_heads            # ranks per KV head: split the batch between them
+        per_b = batch // ways
+        head, part = rank // ways, rank % ways
+        return HeadShard(rank, world_size, num_heads, num_kv_heads, batch, head, head + 1, part * per_b,
+                         (part + 1) * per_b)
+    raise ValueError(
+        f"cannot shard {num_kv_heads} KV heads x batch {batch} evenly over {world_size} ranks "
+        "(need Hkv % W == 0, or W % Hkv == 0 with batch divisible by W / Hkv)")
+
+
+def shard_kv_heads(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, shard: HeadShard):
+    """Slice full (B, H, N, D) q/k/v down to this rank's heads (views, no copy)."""
+    qs = q[shard.b_start:shard.b_end, shard.q_start:shard.q_end]
+    ks = k[shard.b_start:shard.b_end, shard.kv_start:shard.kv_end]
+    vs = v[shard.b_start:shard.b_end, shard.kv_start:shard.kv_end]
+    return qs, ks, vs
+
+
+def gather_heads(o_local: torch.Tensor, shard: HeadShard, group=None) -> torch.Tensor:
+    """All-gather head-sharded outputs (B_loc, Hq_loc, ...) into the full (B, Hq, ...) tensor.
+
+    One `all_gather_into_tensor` over NCCL (NVLink 5 / NVSwitch) on GPU tensors, gloo on CPU tensors
+    in tests; the rank-major result is permuted back to head order locally."""
+    W = shard.world_size
+    if W == 1:
+        return o_local
+    x = o_local.contiguous()
+    buf = torch.empty((W, *x.shape), dtype=x.dtype, device=x.device)
+    try:
+        dist.all_gather_into_tensor(buf, x, group=group)
+    except (RuntimeError, NotImplementedError):
+        parts = [torch.empty_like(x) for _ in range(W)]
+        dist.all_gather(parts, x, group=group)
+        buf = torch.stack(parts, 0)
+    if shard.num_kv_heads % W == 0:
+        # (W, B, Hq/W, ...) -> (B, W, Hq/W, ...) -> (B, Hq, ...)
+        return buf.transpose(0, 1).reshape(x.shape[0], W * x.shape[1], *x.shape[2:])
+    ways = W // shard.num_kv_heads
+    # rank = head * ways + part: (Hkv, ways, B/ways, G, ...) -> (ways, B/ways, Hkv, G, ...) -> (B, Hq, ...)
+    buf = buf.reshape(shard.num_kv_heads, ways, *x.shape)
+    buf = buf.permute(1, 2, 0, 3, *range(4, buf.dim()))
+    return buf.reshape(shard.batch, shard.num_heads, *x.shape[2:])
+
+
+def init_distributed(backend: str | None = None):
+    """Join the process group described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun).
+    Returns (rank, world_size, local_rank).  Single-process runs return (0, 1, 0) without a group."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend)
+    return rank, world, local

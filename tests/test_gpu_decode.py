@@ -1,0 +1,196 @@
+"""GPU parity tests of the decode path (contiguous ch02 cache and ch07 paged pools), the KV append
+and the page addressing, through the C ABI, against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import physics_llm_inference_b200 as pli
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2, torch.float16: 2e-2}
+LSE_TOL = 1e-3
+
+
+def _paged_case(seed, B, Hq, Hkv, D, bs, lens, dtype, n_layers=1, layer=0, num_splits=None):
+    q, kp, vp, table, lens_t = orc.seeded_paged(seed, B, Hq, Hkv, D, bs, lens, num_layers=n_layers)
+    qd, kd, vd = q.to(dtype).cuda(), kp.to(dtype).cuda(), vp.to(dtype).cuda()
+    o, lse = pli.flash_decode(qd, kd, vd, lens_t.cuda(), block_tables=table.cuda(), layer=layer, return_lse=True,
+                              num_splits=num_splits, max_seq_len=max(lens))
+    torch.cuda.synchronize()
+    ro, rlse = orc.paged_decode_oracle(qd, kd, vd, table, lens_t, layer=layer)
+    assert o.shape == qd.shape and o.dtype == dtype
+    return (o.float().cpu() - ro).abs().max().item(), (lse.cpu() - rlse[:, :, 0]).abs().max().item(), kd, table
+
+
+@pytest.mark.parametrize("bs,D,G", [(16, 32, 4), (16, 128, 4), (7, 48, 2), (32, 64, 1)])
+def test_paged_decode_fp32_simt(bs, D, G):
+    eo, el, kd, table = _paged_case(31, 3, 2 * G, 2, D, bs, [77, bs, 1], torch.float32, n_layers=2, layer=1)
+    assert pli.decode_kernel_kind(kd, table) == "simt"
+    assert eo <= TOL[torch.float32] and el <= LSE_TOL, (eo, el)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("bs,D,G,lens,splits", [
+    (16, 128, 4, [4096, 100, 1, 17, 2048], None),      # C3-shaped pages, ragged batch
+    (16, 128, 4, [1000, 999], 1),
+    (16, 128, 4, [1000, 999], 7),
+    (16, 64, 8, [513, 64, 65], None),
+    (8, 128, 1, [300, 9], 2),                          # MHA, small pages
+    (64, 128, 2, [700, 64, 1], None),
+    (128, 64, 16, [900, 128, 129], 3),                 # pages larger than a stage, 16 q heads per kv head
+    (256, 128, 4, [1025], None),
+    (16, 128, 32, [555, 16], 2),                       # 32 q heads per kv head: two 16-row chunks
+])
+def test_paged_decode_tma(bs, D, G, lens, splits, dtype):
+    eo, el, kd, table = _paged_case(32, len(lens), 2 * G, 2, D, bs, lens, dtype, n_layers=2, layer=1, num_splits=splits)
+    assert pli.decode_kernel_kind(kd, table) == "mma_tma"
+    assert eo <= TOL[dtype] and el <= LSE_TOL, (eo, el)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_contiguous_decode(dtype):
+    B, Hq, Hkv, D, Lmax = 3, 8, 2, 128, 700
+    g = torch.Generator().manual_seed(33)
+    q = torch.randn(B, Hq, 1, D, generator=g).to(dtype).cuda()
+    kc = torch.randn(B, Lmax, Hkv, D, generator=g).to(dtype).cuda()
+    vc = torch.randn(B, Lmax, Hkv, D, generator=g).to(dtype).cuda()
+    for L in (1, 63, 64, 65, 500, 700):
+        o, lse = pli.flash_decode(q, kc, vc, L, return_lse=True)
+        ro, rlse = orc.cached_attention_oracle(q, kc, vc, L)
+        assert (o.float().cpu() - ro).abs().max().item() <= TOL[dtype], L
+        assert (lse.cpu() - rlse[:, :, 0]).abs().max().item() <= LSE_TOL, L
+    lens = torch.tensor([700, 3, 257], dtype=torch.int32)
+    o = pli.flash_decode(q, kc, vc, lens.cuda())
+    ro, _ = orc.cached_attention_oracle(q, kc, vc, lens)
+    assert (o.float().cpu() - ro).abs().max().item() <= TOL[dtype]
+
+
+def test_garbage_beyond_seq_len_is_never_used():
+    """Storage past seq_len (rest of the last page, unused pages) may hold NaN/Inf: results must not change."""
+    B, Hq, Hkv, D, bs = 2, 8, 2, 128, 16
+    lens = [100, 37]
+    q, kp, vp, table, lens_t = orc.seeded_paged(34, B, Hq, Hkv, D, bs, lens)
+    kd, vd = kp.bfloat16().cuda(), vp.bfloat16().cuda()
+    o0 = pli.flash_decode(q.bfloat16().cuda(), kd, vd, lens_t.cuda(), block_tables=table.cuda())
+    used = torch.zeros(kd.shape[0], bs, dtype=torch.bool)
+    for b, L in enumerate(lens):
+        for t in range(L):
+            used[int(table[b, t // bs]), t % bs] = True
+    kd[~used.cuda()] = float("nan")
+    vd[~used.cuda()] = float("inf")
+    o1 = pli.flash_decode(q.bfloat16().cuda(), kd, vd, lens_t.cuda(), block_tables=table.cuda())
+    assert torch.equal(o0, o1)
+
+
+def test_page_addressing_bit_exact():
+    """token t -> page table[t // bs], slot t % bs (ch07/paged_memory.py:54,84-86), bit for bit."""
+    B, Hkv, D, bs, n_layers = 3, 2, 64, 16, 3
+    lens = [50, 16, 33]
+    _, kp, _, table, lens_t = orc.seeded_paged(35, B, 4, Hkv, D, bs, lens, num_layers=n_layers)
+    for dtype in (torch.float32, torch.bfloat16):
+        pool = kp.to(dtype).cuda()
+        for layer in range(n_layers):
+            got = pli.paged_gather(pool, table.cuda(), lens_t.cuda(), max(lens), layer=layer).cpu()
+            for b, L in enumerate(lens):
+                ref = orc.gather_paged(pool.cpu(), table[b].tolist(), L, layer)
+                assert torch.equal(got[b, :L], ref)
+                assert torch.count_nonzero(got[b, L:]) == 0
+
+
+def test_kv_append_roundtrip_and_reference_objects(golden_dir):
+    """ch02 golden: prefill 37, chunk 11, decode 1, decode 1 through KVCache.update + the kernels."""
+    g = np.load(os.path.join(golden_dir, "ch02_cached.npz"))
+    B, Hq, Hkv, D, Lmax = [int(x) for x in g["meta"]]
+    cache = pli.KVCache.create(B, Lmax, Hkv, D, torch.device("cuda"), torch.float32)
+    layer_cache = pli.create_caches(1, B, Lmax, Hkv, D, "cuda", torch.float32)[0]
+    for step in range(4):
+        x = torch.from_numpy(g[f"x{step}"]).cuda()
+        s = x.shape[1]
+        q = x.view(B, s, Hq, D).transpose(1, 2)
+        k_new = x[..., :Hkv * D].reshape(B, s, Hkv, D)
+        v_new = x[..., Hkv * D:2 * Hkv * D].reshape(B, s, Hkv, D)
+        k_full, v_full = cache.update(k_new, v_new)
+        layer_cache.update(k_new, v_new)
+        assert k_full.shape[1] == cache.seq_len == layer_cache.seq_len
+        ref = torch.from_numpy(g[f"y{step}"])
+        if s > 1:   # chunk over the cache: offset causal mask (ch02/cached_generation.py:85-91)
+            o = pli.flash_attention_forward(q, k_full.transpose(1, 2), v_full.transpose(1, 2), causal=True)
+        else:
+            o = pli.decode_with_cache(q, cache)
+            o2 = pli.decode_with_cache(q, layer_cache)
+            assert torch.equal(o, o2)
+        assert (o.cpu() - ref).abs().max().item() <= 1e-3, step
+    assert torch.equal(cache.k_cache.cpu(), torch.from_numpy(g["k_cache"]))
+    assert torch.equal(cache.v_cache.cpu(), torch.from_numpy(g["v_cache"]))
+    assert torch.equal(layer_cache.k, cache.k_cache)
+
+
+def test_golden_paged_decode(golden_dir):
+    g = np.load(os.path.join(golden_dir, "paged_decode.npz"))
+    seed, B, Hq, Hkv, D, bs, n_layers, layer = [int(x) for x in g["meta"]]
+    lens = [int(x) for x in g["lens"]]
+    q, kp, vp, table, lens_t = orc.seeded_paged(seed, B, Hq, Hkv, D, bs, lens, num_layers=n_layers)
+    o, lse = pli.flash_decode(q.cuda(), kp.cuda(), vp.cuda(), lens_t.cuda(), block_tables=table.cuda(), layer=layer,
+                              return_lse=True)
+    assert (o.cpu() - torch.from_numpy(g["o"])).abs().max().item() <= 1e-3
+    assert (lse.cpu() - torch.from_numpy(g["lse"])[:, :, 0]).abs().max().item() <= 1e-3
+
+
+def test_paged_cache_object_write_then_read():
+    """PagedKVCache mirror end to end: allocate -> append (kernel) -> decode (kernel) == oracle."""
+    Hq, Hkv, D, bs, layers = 8, 2, 128, 16, 2
+    cache = pli.PagedKVCache(num_blocks=64, block_size=bs, num_layers=layers, num_heads=Hkv, head_dim=D,
+                             dtype=torch.bfloat16, device="cuda")
+    g = torch.Generator().manual_seed(36)
+    lens = {10: 45, 11: 16, 12: 1}
+    kv = {}
+    for rid, L in lens.items():
+        ks = torch.randn(1, L, Hkv, D, generator=g).bfloat16().cuda()
+        vs = torch.randn(1, L, Hkv, D, generator=g).bfloat16().cuda()
+        cache.append([rid], ks[:, :L - 1], vs[:, :L - 1], layer=1) if L > 1 else None
+        cache.append([rid], ks[:, L - 1:], vs[:, L - 1:], layer=1)          # grows by one token (extend_blocks)
+        kv[rid] = (ks, vs)
+        assert cache.block_tables[rid].num_tokens == L
+        assert cache.block_tables[rid].num_blocks() == (L + bs - 1) // bs
+    rids = list(lens)
+    q = torch.randn(len(rids), Hq, 1, D, generator=g).bfloat16().cuda()
+    o = pli.decode_with_paged(q, cache, rids, layer=1)
+    for i, rid in enumerate(rids):
+        ro, _ = orc.cached_attention_oracle(q[i:i + 1], kv[rid][0], kv[rid][1], lens[rid])
+        assert (o[i:i + 1].float().cpu() - ro).abs().max().item() <= 2e-2
+    assert torch.count_nonzero(cache.k_cache[:, 0]) == 0                    # layer 0 untouched
+    freed = cache.free_blocks_for_request(10)
+    assert freed == 3 and cache.get_num_free_blocks() == 64 - 1 - 1
+
+
+def test_c3_full_size_properties():
+    """BASELINE C3 (B64, ctx 4096, 32q/8kv, D128, 16-token pages): sampled sequences vs the oracle,
+    V = 1 => O = 1, and invariance under a re-permutation of the physical pages."""
+    B, Hq, Hkv, D, bs, L = 64, 32, 8, 128, 16, 4096
+    pages_per = L // bs
+    P = B * pages_per + 5
+    g = torch.Generator(device="cuda").manual_seed(37)
+    kp = torch.randn(P, 1, bs, Hkv, D, device="cuda", generator=g).bfloat16()
+    vp = torch.randn(P, 1, bs, Hkv, D, device="cuda", generator=g).bfloat16()
+    q = torch.randn(B, Hq, 1, D, device="cuda", generator=g).bfloat16()
+    perm = torch.randperm(P, generator=torch.Generator().manual_seed(38))[:B * pages_per].to(torch.int32)
+    table = perm.view(B, pages_per).cuda()
+    lens = torch.full((B,), L, dtype=torch.int32, device="cuda")
+    o, lse = pli.flash_decode(q, kp, vp, lens, block_tables=table, return_lse=True, max_seq_len=L)
+    for b in (0, 31, 63):
+        ro, rlse = orc.paged_decode_oracle(q[b:b + 1], kp, vp, table[b:b + 1].cpu(), [L])
+        assert (o[b:b + 1].float().cpu() - ro).abs().max().item() <= 2e-2
+        assert (lse[b:b + 1].cpu() - rlse[:, :, 0]).abs().max().item() <= 1e-3
+    o1 = pli.flash_decode(q, kp, torch.ones_like(vp), lens, block_tables=table, max_seq_len=L)
+    assert (o1.float() - 1).abs().max().item() <= 1e-2
+    # move every page somewhere else: same logical cache, different physical layout => identical output
+    perm2 = torch.randperm(P, generator=torch.Generator().manual_seed(39))
+    inv = torch.empty_like(perm2)
+    inv[perm2] = torch.arange(P)
+    kp2, vp2 = kp[perm2.cuda()], vp[perm2.cuda()]          # new_pool[i] = old_pool[perm2[i]]
+    table2 = inv.cuda()[table.long()].to(torch.int32)
+    o2 = pli.flash_decode(q, kp2, vp2, lens, block_tables=table2, max_seq_len=L)
+    assert torch.equal(o2, o)

@@ -1,0 +1,197 @@
+"""GPU parity tests of the prefill path, through the C ABI, against the CPU oracle.
+
+Tolerances are BASELINE.json's: max-abs-error 2e-2 for bf16/f16 inputs, 1e-3 for f32 inputs, 1e-3
+for log-sum-exp, all against the oracle run in fp32 on the same (already rounded) inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import physics_llm_inference_b200 as pli
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2, torch.float16: 2e-2}
+LSE_TOL = 1e-3
+
+
+def _run(q, k, v, causal, scale=None, dtype=torch.bfloat16):
+    qd, kd, vd = (x.to(dtype).cuda() for x in (q, k, v))
+    o, lse = pli.flash_attention_forward(qd, kd, vd, scale, causal=causal, return_lse=True)
+    torch.cuda.synchronize()
+    ro, rlse = orc.flash_attention_oracle(qd, kd, vd, scale, causal=causal)   # oracle sees the rounded inputs
+    assert o.shape == qd.shape and o.dtype == dtype and lse.shape == qd.shape[:3]
+    return (o.float().cpu() - ro).abs().max().item(), (lse.cpu() - rlse).abs().max().item()
+
+
+def test_umma_selftest_descriptors():
+    """One 128x128xD tile through the SS (K-major) and TS (MN-major B) MMA paths of the kernel."""
+    from physics_llm_inference_b200 import _lib
+    lib = _lib.load()
+    for D in (128, 64):
+        for dtype in (torch.bfloat16, torch.float16):
+            g = torch.Generator().manual_seed(5)
+            a = torch.randn(128, D, generator=g).to(dtype).cuda()
+            b = torch.randn(128, D, generator=g).to(dtype).cuda()
+            c = torch.randn(128, D, generator=g).to(dtype).cuda()
+            s_out = torch.zeros(128, 128, device="cuda")
+            o_out = torch.zeros(128, D, device="cuda")
+            _lib.check(lib.pli_set_device(0))
+            _lib.check(lib.pli_debug_umma_selftest(a.data_ptr(), b.data_ptr(), c.data_ptr(), s_out.data_ptr(),
+                                                   o_out.data_ptr(), D, _lib.dtype_code(dtype),
+                                                   torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+            s_ref = a.float() @ b.float().T
+            assert (s_out - s_ref).abs().max().item() < 1e-3, f"SS K-major MMA wrong (D={D}, {dtype})"
+            p = (s_out * 0.015625).to(dtype).float()
+            o_ref = p @ c.float()
+            assert (o_out - o_ref).abs().max().item() < 2e-3, f"TS MN-major MMA wrong (D={D}, {dtype})"
+
+
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("shape", [(1, 8, 8, 512, 512, 64), (2, 4, 2, 100, 100, 32), (1, 2, 1, 33, 77, 16),
+                                   (1, 3, 3, 70, 70, 128), (1, 2, 2, 40, 40, 80)])
+def test_fp32_simt_parity(shape, causal):
+    B, Hq, Hkv, Nq, Nk, D = shape
+    q, k, v = orc.seeded_qkv(0xC0FFEE + 1, B, Hq, Hkv, Nq, Nk, D)
+    assert pli.prefill_kernel_kind(q.cuda(), k.cuda(), v.cuda()) == "simt"
+    eo, el = _run(q, k, v, causal, dtype=torch.float32)
+    assert eo <= TOL[torch.float32] and el <= LSE_TOL, (eo, el)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("shape", [
+    (1, 8, 8, 512, 512, 64),        # C1 shape (book test shape) in 16-bit
+    (2, 4, 4, 128, 128, 64),        # ch06/test_ch06.py:160-178
+    (1, 4, 1, 256, 256, 128),       # one work item, two full Q tiles, GQA 4:1
+    (2, 8, 2, 1024, 1024, 128),     # C2 scaled down
+    (1, 4, 2, 300, 300, 128),       # ragged tiles
+    (1, 2, 2, 1, 1, 128),           # single token
+    (1, 4, 2, 77, 333, 64),         # Nq < Nk: bottom-right aligned mask (chunk over cache)
+    (1, 8, 2, 129, 1000, 128),
+    (3, 6, 3, 513, 513, 128),
+])
+def test_tcgen05_parity(shape, causal, dtype):
+    B, Hq, Hkv, Nq, Nk, D = shape
+    q, k, v = orc.seeded_qkv(0xC0FFEE + 2, B, Hq, Hkv, Nq, Nk, D)
+    assert pli.prefill_kernel_kind(q.to(dtype).cuda(), k.to(dtype).cuda(), v.to(dtype).cuda()) == "tcgen05"
+    eo, el = _run(q, k, v, causal, dtype=dtype)
+    assert eo <= TOL[dtype] and el <= LSE_TOL, (eo, el)
+
+
+def test_reference_cuda_tests_pass_against_the_drop_in():
+    """ch06/test_ch06.py:160-189 verbatim (fp16, rtol=atol 0.01 / 0.02 vs naive attention)."""
+    torch.manual_seed(0)
+    for (B, H, N, D), tol in [((2, 4, 128, 64), 0.01), ((1, 8, 512, 64), 0.02), ((2, 8, 256, 64), 0.01)]:
+        q = torch.randn(B, H, N, D, device="cuda", dtype=torch.float16)
+        k = torch.randn(B, H, N, D, device="cuda", dtype=torch.float16)
+        v = torch.randn(B, H, N, D, device="cuda", dtype=torch.float16)
+        out = pli.flash_attention_forward(q, k, v)
+        assert out.shape == (B, H, N, D)
+        naive, _ = orc.naive_attention_oracle(q, k, v)
+        torch.testing.assert_close(out.float().cpu(), naive, rtol=tol, atol=tol)
+
+
+def test_golden_c1_fp32(golden_dir):
+    """BASELINE config 1 against the stored output of the unmodified reference."""
+    g = np.load(os.path.join(golden_dir, "ch06_flash.npz"))
+    seed, B, H, N, D, stride = [int(x) for x in g["c1_meta"]]
+    q, k, v = orc.seeded_qkv(seed, B, H, H, N, N, D)
+    o = pli.flash_attention_forward(q.cuda(), k.cuda(), v.cuda())
+    ref = torch.from_numpy(g["c1_flash"])
+    assert (o.cpu()[:, :, ::stride] - ref).abs().max().item() <= 1e-3
+    for dtype in (torch.bfloat16, torch.float16):       # same inputs rounded: 2e-2 against the fp32 reference run
+        o = pli.flash_attention_forward(q.to(dtype).cuda(), k.to(dtype).cuda(), v.to(dtype).cuda())
+        assert (o.float().cpu()[:, :, ::stride] - ref).abs().max().item() <= 2e-2
+
+
+def test_golden_ch01_gqa_and_ch02_chunks(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ch01_gqa.npz"))
+    B, Hq, Hkv, N, D = [int(x) for x in g["meta"]]
+    x = torch.from_numpy(g["x"]).cuda()
+    # the (B,N,H,D)->(B,H,N,D) transposed views of ch01/gqa.py:27-29 go in without a copy
+    q = x.view(B, N, Hq, D).transpose(1, 2)
+    k = x[..., :Hkv * D].reshape(B, N, Hkv, D).transpose(1, 2)
+    v = x[..., Hkv * D:2 * Hkv * D].reshape(B, N, Hkv, D).transpose(1, 2)
+    o = pli.flash_attention_forward(q, k, v, causal=True)
+    assert (o.cpu() - torch.from_numpy(g["causal"])).abs().max().item() <= 1e-3
+    o = pli.flash_attention_forward(q, k, v)
+    assert (o.cpu() - torch.from_numpy(g["full"])).abs().max().item() <= 1e-3
+
+
+def test_strided_views_bf16():
+    """(B,N,H,D) storage viewed as (B,H,N,D): TMA descriptors are built from the strides."""
+    B, N, Hq, Hkv, D = 2, 384, 8, 2, 128
+    g = torch.Generator().manual_seed(9)
+    qs = torch.randn(B, N, Hq, D, generator=g).bfloat16().cuda()
+    ks = torch.randn(B, N, Hkv, D, generator=g).bfloat16().cuda()
+    vs = torch.randn(B, N, Hkv, D, generator=g).bfloat16().cuda()
+    q, k, v = qs.transpose(1, 2), ks.transpose(1, 2), vs.transpose(1, 2)
+    assert pli.prefill_kernel_kind(q, k, v) == "tcgen05"
+    o = pli.flash_attention_forward(q, k, v, causal=True)
+    assert o.stride() == q.stride()
+    ro, _ = orc.flash_attention_oracle(q, k, v, causal=True)
+    assert (o.float().cpu() - ro).abs().max().item() <= 2e-2
+
+
+def test_scale_and_config_arguments():
+    q, k, v = orc.seeded_qkv(21, 1, 4, 4, 200, 200, 64)
+    for dtype in (torch.float32, torch.bfloat16):
+        qd, kd, vd = (x.to(dtype).cuda() for x in (q, k, v))
+        for scale in (0.2, 1.0, -0.1):
+            o = pli.flash_attention_forward(qd, kd, vd, scale, pli.FlashAttentionConfig(block_q=48, block_k=80))
+            ro, _ = orc.flash_attention_oracle(qd, kd, vd, scale)
+            assert (o.float().cpu() - ro).abs().max().item() <= (3e-2 if scale == 1.0 else TOL[dtype])
+
+
+def test_normalisation_and_causality_properties_full_size():
+    """Size-independent properties at BASELINE's C2 shape (B4, 32q/8kv, N8192, D128, bf16, causal)."""
+    B, Hq, Hkv, N, D = 4, 32, 8, 8192, 128
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(B, Hq, N, D, device="cuda", generator=g).bfloat16()
+    k = torch.randn(B, Hkv, N, D, device="cuda", generator=g).bfloat16()
+    v = torch.randn(B, Hkv, N, D, device="cuda", generator=g).bfloat16()
+    o, lse = pli.flash_attention_forward(q, k, v, causal=True, return_lse=True)
+    # (1) V = 1 => O = 1 exactly up to bf16 rounding (ch06/test_ch06.py:67-73)
+    ones = torch.ones_like(v)
+    o1 = pli.flash_attention_forward(q, k, ones, causal=True)
+    assert (o1.float() - 1).abs().max().item() <= 1e-2
+    # (2) causality by perturbation (ch01/test_ch01.py:22-39): changing the last 100 keys/values leaves earlier rows bit-identical
+    k2, v2 = k.clone(), v.clone()
+    k2[:, :, -100:] += 3
+    v2[:, :, -100:] -= 2
+    o2 = pli.flash_attention_forward(q, k2, v2, causal=True)
+    assert torch.equal(o2[:, :, :N - 100], o[:, :, :N - 100])
+    assert not torch.equal(o2[:, :, N - 100:], o[:, :, N - 100:])
+    # (3) sampled rows against the oracle (fp32, CPU): every 4th head of two batches, 24 rows spread over N
+    rows = torch.tensor([0, 1, 127, 128, 129, 255, 256, 1000, 2047, 2048, 4095, 4096, 4097, 5000, 6143, 6144, 7000,
+                         7935, 7936, 8063, 8064, 8100, 8190, 8191])
+    G = Hq // Hkv
+    for b in (0, 3):
+        for h in range(0, Hq, 4):
+            kk = k[b, h // G].float().cpu()
+            vv = v[b, h // G].float().cpu()
+            s = (q[b, h, rows.cuda()].float().cpu() @ kk.T) * D ** -0.5
+            s = s.masked_fill(torch.arange(N)[None, :] > rows[:, None], float("-inf"))
+            ref = torch.softmax(s, -1) @ vv
+            assert (o[b, h, rows.cuda()].float().cpu() - ref).abs().max().item() <= 2e-2
+            assert (lse[b, h, rows.cuda()].cpu() - torch.logsumexp(s, -1)).abs().max().item() <= LSE_TOL
+    # (4) GQA map: q heads 4j..4j+3 with identical q rows give identical outputs (they share kv head j)
+    qq = q.clone()
+    qq[:, 1::4] = qq[:, 0::4]
+    oo = pli.flash_attention_forward(qq, k, v, causal=True)
+    assert torch.equal(oo[:, 1::4], oo[:, 0::4])
+
+
+def test_errors_on_gpu_tensors():
+    q = torch.randn(1, 6, 16, 64, device="cuda").bfloat16()
+    k = torch.randn(1, 4, 16, 64, device="cuda").bfloat16()
+    with pytest.raises(RuntimeError, match="multiple"):
+        pli.flash_attention_forward(q, k, k)
+    with pytest.raises(ValueError, match="Nq <= Nk"):
+        pli.flash_attention_forward(q, q[:, :, :8], q[:, :, :8], causal=True)
+    with pytest.raises(RuntimeError, match="dtype"):
+        pli.flash_attention_forward(q, q.float(), q.float())

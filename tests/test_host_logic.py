@@ -1,0 +1,160 @@
+"""CPU tests of the host side: the reference-facing interface, the allocator mirror against the
+reference's golden trace, accounting conventions, the C-ABI exports, and loud failure without CUDA."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import physics_llm_inference_b200 as pli
+from physics_llm_inference_b200 import _lib
+
+
+def test_library_exports_every_header_symbol():
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert len(names) >= 14
+    for name in names:
+        assert hasattr(lib, name), f"{name} is declared in include/pli_attention.h but not exported"
+        assert name in _lib._SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.pli_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in names:
+        assert f" T {name}" in out
+
+
+def test_library_is_sm100a_native():
+    """The shipped cubin carries tcgen05 / TMA instructions (SASS mnemonics from B200_PROFILING.md)."""
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass          # tcgen05.mma
+    assert "LDTM" in sass and "STTM" in sass   # tcgen05.ld / st
+    assert "UTMALDG" in sass and "UTMASTG" in sass  # TMA load / store
+
+
+def test_workspace_and_split_helpers_need_no_gpu():
+    lib = _lib.load()
+    assert lib.pli_decode_workspace_bytes(64, 32, 128, 4) == 64 * 32 * 4 * 129 * 4
+    assert lib.pli_decode_workspace_bytes(0, 32, 128, 4) == 0
+
+
+def test_config_defaults_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ch06_flash.npz"))
+    cfg = pli.FlashAttentionConfig()
+    assert [cfg.block_q, cfg.block_k, cfg.num_warps, cfg.num_stages] == [int(x) for x in g["config_defaults"]]
+    assert pli.attention_flops(1, 8, 512, 64) == int(g["flops_c1"][0])
+    assert pli.flash_attention_memory_bytes(1, 8, 512, 64)["hbm_bytes"] == int(g["membytes_c1"][0])
+    mem = pli.flash_attention_memory_bytes(batch_size=1, num_heads=8, seq_len=1024, head_dim=64)
+    assert mem["hbm_bytes"] < mem["naive_hbm_bytes"]            # ch06/test_ch06.py:143-151
+
+
+def test_algorithmic_flops_convention():
+    # C2 = 2.199 TFLOP, C1 = 0.537 GFLOP (0.268 causal)
+    assert abs(pli.prefill_algorithmic_flops(4, 32, 8192, 8192, 128, True) - 2.199e12) < 1e9
+    assert abs(pli.prefill_algorithmic_flops(1, 8, 512, 512, 64, False) - 0.537e9) < 1e6
+    assert abs(pli.prefill_algorithmic_flops(1, 8, 512, 512, 64, True) - 0.268e9) < 1e6
+
+
+def test_cpu_tensors_fail_loudly():
+    q = torch.randn(1, 2, 8, 16)
+    with pytest.raises(RuntimeError, match="no\\s+CPU fallback"):
+        pli.flash_attention_forward(q, q, q)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pli.flash_decode(q[:, :, :1], torch.zeros(1, 8, 2, 16), torch.zeros(1, 8, 2, 16), 8)
+    with pytest.raises(RuntimeError):
+        pli.KVCache.create(1, 8, 2, 16, torch.device("cpu"), torch.float32).update(torch.zeros(1, 1, 2, 16),
+                                                                                     torch.zeros(1, 1, 2, 16))
+
+
+def test_signature_matches_reference():
+    import inspect
+    sig = inspect.signature(pli.flash_attention_forward)
+    names = list(sig.parameters)
+    assert names[:5] == ["q", "k", "v", "scale", "config"]        # ch06/flash_attention.py:14-20
+    assert sig.parameters["scale"].default is None and sig.parameters["config"].default is None
+    assert sig.parameters["causal"].kind is inspect.Parameter.KEYWORD_ONLY
+    assert sig.parameters["causal"].default is False              # default stays non-causal
+    assert sig.parameters["return_lse"].kind is inspect.Parameter.KEYWORD_ONLY
+    assert pli.flash_attention is pli.flash_attention_forward
+
+
+def test_shape_validation_errors():
+    # validation happens before any CUDA call, so the messages can be checked on CPU tensors too
+    q = torch.randn(2, 8, 4)
+    with pytest.raises(RuntimeError, match=r"\(B, H, N, D\)"):
+        pli.flash_attention_forward(q, q, q)
+
+
+# ---- ch07 allocator mirror vs the reference's recorded behaviour ----
+def test_paged_allocator_matches_reference_trace(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ch07_paged.npz"))
+    c = pli.PagedKVCache(num_blocks=20, block_size=16, num_layers=2, num_heads=4, head_dim=64, device="cpu")
+    assert c.k_cache is None and c.v_cache is None
+    for op, rid, n, err, nblocks, ntok, nfree in g["trace"].tolist():
+        got = 0
+        try:
+            if op == 0:
+                c.allocate_blocks(rid, n)
+            elif op == 1:
+                c.extend_blocks(rid, n)
+            else:
+                c.free_blocks_for_request(rid)
+        except RuntimeError:
+            got = 1
+        except KeyError:
+            got = 2
+        assert got == err, (op, rid, n)
+        t = c.block_tables.get(rid)
+        assert (-1 if t is None else t.num_blocks()) == nblocks
+        assert (-1 if t is None else t.num_tokens) == ntok
+        assert c.get_num_free_blocks() == nfree
+    u = c.get_memory_usage()
+    assert [u["total_blocks"], u["used_blocks"], u["free_blocks"], u["block_size_tokens"], u["bytes_per_block"]] == \
+        [int(x) for x in g["usage"]]
+    bt = pli.BlockTable(request_id=7, block_indices=[3, 1, 2], num_tokens=40)
+    assert [bt.request_id, bt.num_blocks(), bt.num_tokens] == [int(x) for x in g["bt"]]
+
+
+def test_paged_reference_unit_tests():
+    """ch07/test_ch07.py:228-323 restated against the mirror."""
+    c = pli.PagedKVCache(num_blocks=100, block_size=16, num_layers=2, num_heads=4, head_dim=64, device="cpu")
+    t = c.allocate_blocks(request_id=1, num_tokens=50)
+    assert (t.request_id, t.num_tokens, len(t.block_indices)) == (1, 50, 4)
+    assert len(set(t.block_indices)) == 4
+    c.extend_blocks(1, 20)
+    assert c.block_tables[1].num_tokens == 70 and len(c.block_tables[1].block_indices) == 5
+    free0 = c.get_num_free_blocks()
+    assert c.free_blocks_for_request(1) == 5 and c.get_num_free_blocks() == free0 + 5
+    assert c.free_blocks_for_request(1) == 0
+    u = c.get_memory_usage()
+    assert u["total_blocks"] == 100 and u["free_blocks"] == 100 and u["utilization"] == 0.0
+    small = pli.PagedKVCache(num_blocks=2, block_size=16, num_layers=2, num_heads=4, head_dim=64, device="cpu")
+    with pytest.raises(RuntimeError):
+        small.allocate_blocks(request_id=1, num_tokens=100)
+    with pytest.raises(KeyError):
+        small.extend_blocks(5, 1)
+
+
+def test_head_sharding_maths():
+    for W in (1, 2, 4, 8):
+        shards = [pli.make_shard(r, W, 32, 8, 4) for r in range(W)]
+        assert sum(s.units for s in shards) == 8 * 4
+        assert [s.kv_start for s in shards] == [r * 8 // W for r in range(W)]
+        for s in shards:
+            assert s.q_start == s.kv_start * 4 and s.q_end == s.kv_end * 4      # consecutive q heads share a kv head
+    s = pli.make_shard(5, 8, 8, 2, 8)                                           # more ranks than kv heads: split batch
+    assert (s.kv_start, s.kv_end, s.b_start, s.b_end) == (1, 2, 2, 4)
+    with pytest.raises(ValueError):
+        pli.make_shard(0, 3, 32, 8, 4)
+
+
+def test_missing_library_is_an_error(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.PliError, match="no CPU fallback"):
+        _lib.load()
