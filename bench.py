@@ -1,0 +1,369 @@
+"""bench.py — the hot path's headline benchmark (BASELINE.json: prefill attn TFLOP/s & paged-decode
+KV GB/s, % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the workload is
+BASELINE config 2 (C2): Llama-3-8B-shaped causal GQA prefill, B4, 32 q / 8 kv heads, D128, N8192,
+bf16 — one `flash_attention_forward` call = one tcgen05 kernel launch.  `value` is whole-job TFLOP/s
+with q/k/v resident in HBM (algorithmic FLOPs 4*B*Hq*N^2*D/2); `e2e` is the same
+metric through the public API with HOST (pinned) buffers, H2D of q,k,v and D2H of O inside the timed
+region.  The second half of the metric, paged decode (C3: B64, ctx 4096, 16-token pages), is timed in
+the same run and reported under `decode` with its own HBM roofline.
+
+N>1 (torchrun, one rank per GPU): attention has no exchange step, so units (batch x KV-head groups)
+are sharded with no data-path collective: each rank runs one C2-sized shard (global batch 4N) —
+`"scaling": "weak"` — and the time is the max over ranks.
+
+`--impl reference`: the reference's CPU implementation of the same path (the oracle port of
+ch06.flash_attention_forward + ch01 mask/GQA; /root/reference does not exist on the GPU box), all
+host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "prefill_attn_tflops"
+UNIT = "TFLOP/s"
+C2 = dict(B=4, Hq=32, Hkv=8, N=8192, D=128)
+C3 = dict(B=64, Hq=32, Hkv=8, L=4096, D=128, bs=16)
+# bounded CPU sample of C2: one of the four batch rows (all 32 q / 8 kv heads), full N, causal
+CPU_SAMPLE = dict(B=1, Hq=32, Hkv=8, N=8192, D=128)
+CPU_DECODE_SAMPLE = dict(B=16, Hq=32, Hkv=8, L=4096, D=128, bs=16)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p.get("bf16_tflops_sustained"),
+                "hbm_gbs": p["hbm_gbs"], "source": "measured"}
+    # B200_PROFILING.md fallback
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def config_dict(n_gpus: int):
+    return {"workload": "C2: causal GQA prefill, 32q/8kv heads, D128, N8192, batch 4 per GPU, bf16",
+            "global_batch": C2["B"] * n_gpus, "seq_len": C2["N"], "heads": f"{C2['Hq']}q/{C2['Hkv']}kv",
+            "head_dim": C2["D"], "causal": True, "parallelism": f"batch x kv-head shard x{n_gpus}, no collective",
+            "l2_policy": "inputs larger than L2 (640 MB of q/k/v/o per step vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML every 10 ms while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.ok:
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.ok:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML sampling unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port), shared by the cpu_baseline key and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_prefill_sample(reps: int = 1):
+    """Oracle restatement of ch06 (+ch01 causal mask and GQA map) on a bounded sample of C2."""
+    import torch
+
+    from oracle import attention_oracle as orc
+    s = CPU_SAMPLE
+    q, k, v = orc.seeded_qkv(0xC0FFEE + 2, s["B"], s["Hq"], s["Hkv"], s["N"], s["N"], s["D"])
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.flash_attention_oracle(q, k, v, causal=True, skip_masked_blocks=True)
+        best = min(best, time.perf_counter() - t0)
+    flops = 4.0 * s["B"] * s["Hq"] * s["N"] * s["N"] * s["D"] / 2
+    return flops / best / 1e12, best, torch.get_num_threads()
+
+
+def cpu_decode_sample():
+    import torch
+
+    from oracle import attention_oracle as orc
+    s = CPU_DECODE_SAMPLE
+    q, kp, vp, table, lens = orc.seeded_paged(0xC0FFEE + 3, s["B"], s["Hq"], s["Hkv"], s["D"], s["bs"],
+                                              [s["L"]] * s["B"])
+    t0 = time.perf_counter()
+    orc.paged_decode_oracle(q, kp, vp, table, lens)
+    dt = time.perf_counter() - t0
+    nbytes = decode_bytes(s["B"], s["Hq"], s["Hkv"], s["L"], s["D"], s["bs"])
+    return nbytes / dt / 1e9, dt, torch.get_num_threads()
+
+
+def decode_bytes(B, Hq, Hkv, L, D, bs, elt=2):
+    """Algorithmic bytes of one decode step: K and V once, q and o, the block table."""
+    return 2 * B * L * Hkv * D * elt + 2 * B * Hq * D * elt + 4 * B * ((L + bs - 1) // bs)
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's CPU path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    s = CPU_SAMPLE
+    for _ in range(min(args.warmup, 1)):
+        cpu_prefill_sample()
+    times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        _, dt, threads = cpu_prefill_sample()
+        times.append(dt)
+    dt = sum(times) / len(times)
+    flops = 4.0 * s["B"] * s["Hq"] * s["N"] * s["N"] * s["D"] / 2
+    val = flops / dt / 1e12
+    sample = (f"oracle port of ch06.flash_attention_forward (+ch01 causal mask, GQA map), fp32, on B{s['B']} x "
+              f"{s['Hq']}q/{s['Hkv']}kv heads x N{s['N']} x D{s['D']} of C2 (1/4 of one GPU's step), "
+              f"{len(times)} timed passes")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded N(0,1))",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host": {"cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import physics_llm_inference_b200 as pli
+
+    rank, world, local = pli.init_distributed("nccl" if world > 1 else None)
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- C2 shard of this rank: synthetic bf16 q/k/v generated on the host (pinned), copied once ----
+    c = C2
+    g = torch.Generator().manual_seed(0xC0FFEE + 2 + rank)
+    host = {}
+    for name, heads in (("q", c["Hq"]), ("k", c["Hkv"]), ("v", c["Hkv"])):
+        t = torch.empty(c["B"], heads, c["N"], c["D"], dtype=torch.bfloat16).pin_memory()
+        t.copy_(torch.randn(c["B"], heads, c["N"], c["D"], generator=g).to(torch.bfloat16))
+        host[name] = t
+    host_o = torch.empty(c["B"], c["Hq"], c["N"], c["D"], dtype=torch.bfloat16).pin_memory()
+    q, k, v = (host[n].to(dev, non_blocking=True) for n in ("q", "k", "v"))
+    torch.cuda.synchronize()
+    flops_step = pli.prefill_algorithmic_flops(c["B"], c["Hq"], c["N"], c["N"], c["D"], True)
+    assert pli.prefill_kernel_kind(q, k, v) == "tcgen05"
+
+    # ---- device-resident timing: W warm-ups, exactly K steps between events ----
+    for _ in range(args.warmup):
+        o = pli.flash_attention_forward(q, k, v, causal=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pli.reset_launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            o = pli.flash_attention_forward(q, k, v, causal=True)
+        e1.record()
+        barrier()
+    launches = pli.launch_count()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    value = flops_step * world / (ms_step * 1e-3) / 1e12
+
+    # ---- end to end through the public API with host buffers (H2D q,k,v; D2H o) ----
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = sum(host[n].numel() * 2 for n in ("q", "k", "v"))
+    d2h = host_o.numel() * 2
+
+    def e2e_step():
+        qd = host["q"].to(dev, non_blocking=True)
+        kd = host["k"].to(dev, non_blocking=True)
+        vd = host["v"].to(dev, non_blocking=True)
+        od = pli.flash_attention_forward(qd, kd, vd, causal=True)
+        host_o.copy_(od, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+    e2e_val = flops_step * world / (e2e_ms * 1e-3) / 1e12
+
+    # ---- second half of the metric: paged decode C3 (device-timed, three pools > L2 rotated) ----
+    decode = None
+    if not args.no_decode:
+        d = C3
+        pages = d["B"] * d["L"] // d["bs"]
+        gd = torch.Generator(device=dev).manual_seed(0xC0FFEE + 3 + rank)
+        pools = [(torch.randn(pages, 1, d["bs"], d["Hkv"], d["D"], device=dev, generator=gd).bfloat16(),
+                  torch.randn(pages, 1, d["bs"], d["Hkv"], d["D"], device=dev, generator=gd).bfloat16())
+                 for _ in range(3)]
+        table = torch.randperm(pages, generator=torch.Generator().manual_seed(5))[:pages].to(torch.int32)
+        table = table.view(d["B"], d["L"] // d["bs"]).to(dev)
+        lens = torch.full((d["B"],), d["L"], dtype=torch.int32, device=dev)
+        qd = torch.randn(d["B"], d["Hq"], 1, d["D"], device=dev, generator=gd).bfloat16()
+        splits = pli.decode_num_splits(d["B"], d["Hkv"], d["L"])
+        ws = pli.decode_workspace(d["B"], d["Hq"], d["D"], splits, dev)
+        out = torch.empty(d["B"], d["Hq"], d["D"], dtype=torch.bfloat16, device=dev)
+        dsteps = max(args.steps, 30)
+        for i in range(max(args.warmup, 3)):
+            pli.flash_decode(qd, *pools[i % 3], lens, block_tables=table, max_seq_len=d["L"], workspace=ws, out=out)
+        barrier()
+        pli.reset_launch_count()
+        e0.record()
+        for i in range(dsteps):
+            pli.flash_decode(qd, *pools[i % 3], lens, block_tables=table, max_seq_len=d["L"], workspace=ws, out=out)
+        e1.record()
+        barrier()
+        d_launches = pli.launch_count()
+        d_ms = max_over_ranks(e0.elapsed_time(e1) / dsteps)
+        nbytes = decode_bytes(d["B"], d["Hq"], d["Hkv"], d["L"], d["D"], d["bs"])
+        gbs = nbytes / (d_ms * 1e-3) / 1e9
+        decode = {"metric": "paged_decode_kv_gbs", "value": gbs * world, "unit": "GB/s", "us_per_step": d_ms * 1e3,
+                  "steps": dsteps, "gpu_launches": int(d_launches), "num_splits": splits,
+                  "config": {"workload": "C3: paged decode, batch 64 per GPU, ctx 4096, 32q/8kv, D128, 16-token pages, bf16",
+                             "l2_policy": "three 1 GiB K/V pool pairs rotated (each larger than L2)"},
+                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
+                               "frac_of_8tbs": gbs / 8000.0, "traffic": None,
+                               "note": "split-KV kernel + combine kernel timed together; algorithmic bytes = K,V once + q,o + table"}}
+        del pools
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (seeded N(0,1), random-init)", "config": config_dict(world),
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "note": "flash_attention_forward on tensors copied from pinned host memory each step; O copied back"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": value / world, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": value / world / peaks["bf16_tflops"],
+                     "peak_source": peaks["source"] + " cuBLAS bf16 burst (kernel timed alone, back to back)",
+                     "frac_of_sustained": (value / world / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
+                     "frac_of_datasheet_2250": value / world / 2250.0, "traffic": None,
+                     "kernel": "prefill_tcgen05_kernel<128,bf16>", "flops_per_launch": flops_step},
+    }
+    if decode is not None:
+        line["decode"] = decode
+    if not args.no_cpu_baseline and world == 1:
+        val, dt, threads = cpu_prefill_sample()
+        s = CPU_SAMPLE
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"oracle port (ch06 recurrence + ch01 mask/GQA, fp32) on B{s['B']} x {s['Hq']}q/{s['Hkv']}kv "
+                                          f"x N{s['N']} x D{s['D']} of C2 = 1/4 of the step, {dt:.1f} s, 1 pass"}
+        if decode is not None:
+            dval, ddt, _ = cpu_decode_sample()
+            s = CPU_DECODE_SAMPLE
+            line["decode"]["cpu_baseline"] = {"value": dval, "unit": "GB/s", "cores": threads, "kind": "port",
+                                              "sample": f"oracle port (ch07 page gather + ch02 cached attention, fp32) on "
+                                                        f"{s['B']} of the 64 sequences, {ddt:.2f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

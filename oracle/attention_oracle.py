@@ -103,7 +103,7 @@ def flash_attention_oracle(
             v_block = v[:, :, k_start:k_end, :]
 
             scores = torch.matmul(q_block, k_block.transpose(-2, -1)) * scale
-            if causal:
+            if causal and k_end - 1 > q_start + off:   # blocks left of the diagonal have nothing to mask
                 kj = torch.arange(k_start, k_end).unsqueeze(0)
                 scores = scores.masked_fill(kj > qi + off, NEG_INF)
 

@@ -155,6 +155,9 @@ struct DecodeTmaParams {
     const int32_t* seq_lens;
     float* o_part;
     float* lse_part;
+    void* o_direct;       // S == 1 only: final output (q's dtype), written instead of the partials
+    float* lse_direct;
+    int64_t osb, osh;
     int64_t qsb, qsh;
     int Hq, Hkv, G, bs, table_stride, layer, S, box_tokens;
     float scale_log2;
@@ -391,9 +394,17 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 den += wt * mg_d[w * 16 + row];
                 o += wt * mg_o[(w * 16 + row) * kD + d];
             }
-            const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
-            p.o_part[prow * kD + d] = den > 0.f ? o / den : 0.f;
-            if (d == 0) p.lse_part[prow] = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
+            const float o_val = den > 0.f ? o / den : 0.f;
+            const float lse_val = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
+            if (p.o_direct != nullptr) {
+                // single split: this CTA owns the whole sequence, so the combine pass is skipped
+                reinterpret_cast<elem_t*>(p.o_direct)[b * p.osb + (h_base + row) * p.osh + d] = from_f32<elem_t>(o_val);
+                if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val;
+            } else {
+                const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
+                p.o_part[prow * kD + d] = o_val;
+                if (d == 0) p.lse_part[prow] = lse_val;
+            }
         }
     }
 }
@@ -526,10 +537,13 @@ using namespace pli;
 
 extern "C" int pli_decode_num_splits(int B, int Hkv, int max_seq_len) {
     if (B <= 0 || Hkv <= 0 || max_seq_len <= 0) return 1;
-    // Aim for ~4 waves of (2 CTAs x SMs) with at least 256 tokens per split.
+    // The kernel is HBM-bound: what matters is enough bytes in flight (2 resident CTAs x 96 KB per SM),
+    // not wave count, and every extra split costs a pipeline fill plus combine traffic (measured on C3:
+    // 1 split 6.2 TB/s, 3 splits 5.5 TB/s).  So split only until one full wave of CTAs exists, with at
+    // least 256 tokens per split.
     const int64_t units = (int64_t)B * Hkv;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    const int64_t target = (int64_t)sms * 2 * 4;
+    const int64_t target = (int64_t)sms * 2;
     int by_fill = (int)((target + units - 1) / units);
     int by_len = (max_seq_len + 255) / 256;
     int s = by_fill < by_len ? by_fill : by_len;
@@ -562,12 +576,14 @@ static int check_decode_args(const void* q, const void* k, const void* v, const 
     return PLI_OK;
 }
 
-extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
-                                  const int32_t* seq_lens, int B, int Hq, int Hkv, int D, int max_seq_len, int block_size,
-                                  int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
-                                  const int64_t kv_strides[4], float scale, int dtype, int num_splits, void* workspace,
-                                  size_t workspace_bytes, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+// Split-KV launch.  When o_direct is given, num_splits == 1 and the TMA kernel serves the request,
+// the kernel writes the final output itself and *wrote_direct is set (the combine pass is not needed).
+static int splitkv_impl(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                        const int32_t* seq_lens, int B, int Hq, int Hkv, int D, int max_seq_len, int block_size,
+                        int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
+                        const int64_t kv_strides[4], float scale, int dtype, int num_splits, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream, void* o_direct, float* lse_direct,
+                        const int64_t* o_strides, bool* wrote_direct) {
     const bool paged = block_table != nullptr;
     if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
     int rc = check_decode_args(q, k_store, v_store, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, paged, num_splits);
@@ -596,6 +612,12 @@ extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void
         p.seq_lens = seq_lens;
         p.o_part = o_part;
         p.lse_part = lse_part;
+        const bool direct = o_direct != nullptr && num_splits == 1;
+        p.o_direct = direct ? o_direct : nullptr;
+        p.lse_direct = direct ? lse_direct : nullptr;
+        p.osb = direct ? o_strides[0] : 0;
+        p.osh = direct ? o_strides[1] : 0;
+        if (wrote_direct) *wrote_direct = direct;
         p.qsb = q_strides[0];
         p.qsh = q_strides[1];
         p.Hq = Hq;
@@ -649,6 +671,16 @@ extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void
     return PLI_OK;
 }
 
+extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                                  const int32_t* seq_lens, int B, int Hq, int Hkv, int D, int max_seq_len, int block_size,
+                                  int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
+                                  const int64_t kv_strides[4], float scale, int dtype, int num_splits, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+    return splitkv_impl(q, k_store, v_store, block_table, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, table_stride,
+                        layer, kv_extent, q_strides, kv_strides, scale, dtype, num_splits, workspace, workspace_bytes,
+                        static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr);
+}
+
 extern "C" int pli_decode_combine(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
                                   const int64_t o_strides[2], int dtype, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -678,10 +710,13 @@ extern "C" int pli_decode_fwd(const void* q, const void* k_store, const void* v_
                               const int64_t kv_strides[4], const int64_t o_strides[2], float scale, int dtype,
                               int num_splits, void* workspace, size_t workspace_bytes, void* stream) {
     if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
-    int rc = pli_decode_splitkv(q, k_store, v_store, block_table, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size,
-                                table_stride, layer, kv_extent, q_strides, kv_strides, scale, dtype, num_splits, workspace,
-                                workspace_bytes, stream);
+    if (!o || !o_strides) return set_error(PLI_ERR_INVALID, "null output argument");
+    bool wrote_direct = false;
+    int rc = splitkv_impl(q, k_store, v_store, block_table, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, table_stride,
+                          layer, kv_extent, q_strides, kv_strides, scale, dtype, num_splits, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), o, lse, o_strides, &wrote_direct);
     if (rc) return rc;
+    if (wrote_direct) return PLI_OK;
     return pli_decode_combine(workspace, o, lse, B, Hq, D, num_splits, o_strides, dtype, stream);
 }
 

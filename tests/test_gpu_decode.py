@@ -79,8 +79,8 @@ def test_garbage_beyond_seq_len_is_never_used():
     for b, L in enumerate(lens):
         for t in range(L):
             used[int(table[b, t // bs]), t % bs] = True
-    kd[~used.cuda()] = float("nan")
-    vd[~used.cuda()] = float("inf")
+    kd[:, 0][~used.cuda()] = float("nan")          # (P, bs) mask over the single layer
+    vd[:, 0][~used.cuda()] = float("inf")
     o1 = pli.flash_decode(q.bfloat16().cuda(), kd, vd, lens_t.cuda(), block_tables=table.cuda())
     assert torch.equal(o0, o1)
 

@@ -1,0 +1,31 @@
+"""Short, fixed workloads for ncu captures (one GPU): `python tools/profile_target.py prefill|decode [reps]`."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import physics_llm_inference_b200 as pli
+
+which = sys.argv[1] if len(sys.argv) > 1 else "prefill"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+torch.manual_seed(0)
+if which == "prefill":
+    B, Hq, Hkv, N, D = 4, 32, 8, 8192, 128
+    q = torch.randn(B, Hq, N, D, device="cuda").bfloat16()
+    k = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
+    v = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
+    for _ in range(reps):
+        pli.flash_attention_forward(q, k, v, causal=True)
+else:
+    B, Hq, Hkv, D, L, bs = 64, 32, 8, 128, 4096, 16
+    P = B * L // bs
+    kp = torch.randn(P, 1, bs, Hkv, D, device="cuda").bfloat16()
+    vp = torch.randn(P, 1, bs, Hkv, D, device="cuda").bfloat16()
+    table = torch.randperm(P)[:P].to(torch.int32).view(B, L // bs).cuda()
+    lens = torch.full((B,), L, dtype=torch.int32, device="cuda")
+    q = torch.randn(B, Hq, 1, D, device="cuda").bfloat16()
+    for _ in range(reps):
+        pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L)
+torch.cuda.synchronize()
+print("done", which)
