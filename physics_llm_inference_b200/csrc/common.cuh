@@ -97,16 +97,12 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
     return t;
 }
+// A failed try_wait returns after a short hardware sleep (~50 cycles measured), so 2^26 spins is a
+// watchdog of a couple of seconds without carrying timer code in every wait site.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
-    uint64_t start = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0xFFF) == 0) {
-            const uint64_t now = global_timer_ns();
-            if (start == 0) start = now;
-            else if (now - start > PLI_MBAR_TIMEOUT_NS) __trap();
-        }
+        if (++spins == (1u << 26)) __trap();
     }
 }
 
@@ -181,6 +177,26 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same, with the 64-bit shared-memory descriptors assembled from a per-operand low word and a shared,
+// compile-time high word (keeps the issuing thread's address arithmetic to one 32-bit add per MMA).
+__device__ __forceinline__ void umma_ss_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed

@@ -316,36 +316,39 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (warp == 8 && lane == 0) tma_store_wait_all<0>();
     } else {
         reg_dealloc<64>();
-        if (warp == 12 && lane == 0) {
+        if (warp == 12) {
             // =========================== MMA issuer ===========================
-            // Descriptor high words are constant: SBO = 1024 B (8 rows x 128 B), version 1, SWIZZLE_128B.
-            constexpr uint64_t kDescHi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
-            constexpr uint64_t kDescK = kDescHi | (uint64_t)(1u << 16);                      // K-major: LBO unused (1)
-            constexpr uint64_t kDescV = kDescHi | ((uint64_t)(kSubTileBytes >> 4) << 16);    // MN-major: LBO = sub-tile
-            const uint32_t sQ_addr = smem_u32(sQ), sKV_addr = smem_u32(sKV);
+            // All 32 lanes run the (warp-uniform) control flow and the waits so the address arithmetic stays
+            // on the uniform datapath; one elected lane issues tcgen05.mma / tcgen05.commit.
+            // Descriptor high word is constant: SBO = 1024 B (8 rows x 128 B), version 1, SWIZZLE_128B.
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t kLboK = 1u << 16;                           // K-major: LBO unused (1)
+            constexpr uint32_t kLboV = (uint32_t)(kSubTileBytes >> 4) << 16;  // MN-major: LBO = one sub-tile
+            const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFFu) | kLboK;
+            const uint32_t k_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboK;
+            const uint32_t v_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboV;
             uint32_t kv_cnt = 0, item_par = 0;
             uint32_t p_par = 0, c_par = 0;                        // bit t: phase parity of p_full[t] / corr_done[t]
-            auto desc_at = [](uint64_t tmpl, uint32_t addr) -> uint64_t { return tmpl | (uint64_t)((addr >> 4) & 0x3FFFu); };
             auto issue_S = [&](int t, uint32_t kslot) {
                 // S_t = Q_t K^T : K-major operands, 16 elements (32 bytes) of head_dim per instruction
-                const uint32_t qa = sQ_addr + t * kTileBytes, ka = sKV_addr + kslot * kTileBytes;
+                const uint32_t qa = q_lo + t * (kTileBytes >> 4), ka = k_lo + kslot * (kTileBytes >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks) {
-                    const uint32_t koff = (ks >> 2) * kSubTileBytes + (ks & 3) * 32;
-                    umma_ss(tmem_base + t * 128, desc_at(kDescK, qa + koff), desc_at(kDescK, ka + koff), kIdescS, ks > 0);
+                    const uint32_t koff = ((ks >> 2) * kSubTileBytes + (ks & 3) * 32) >> 4;
+                    umma_ss_lohi(tmem_base + t * 128, qa + koff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
                 }
             };
             auto issue_PV = [&](int t, uint32_t vslot, uint32_t accumulate) {
                 // O_t += P_t V : A = P from TMEM (8 columns per 16 keys), B = V MN-major (16 keys = 2048 B)
-                const uint32_t va = sKV_addr + vslot * kTileBytes;
+                const uint32_t va = v_lo + vslot * (kTileBytes >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kBN / 16; ++ks)
-                    umma_ts(tmem_base + 256 + t * 128, tmem_base + t * 128 + ks * 8, desc_at(kDescV, va + ks * 2048),
-                            kIdescO, ks > 0 ? 1u : accumulate);
+                    umma_ts_lohi(tmem_base + 256 + t * 128, tmem_base + t * 128 + ks * 8, va + ks * (2048 >> 4), kDescHi,
+                                 kIdescO, ks > 0 ? 1u : accumulate);
             };
             for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
-                const int n_max = it.n[1];
+                const int n0 = it.n[0], n1 = it.n[1];
                 auto slot_of = [&](uint32_t idx) -> uint32_t { return (kv_cnt + idx) % kStages; };
                 auto wait_kv = [&](uint32_t idx) {
                     mbar_wait(&kv_full[(kv_cnt + idx) % kStages], ((kv_cnt + idx) / kStages) & 1);
@@ -356,15 +359,19 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 for (int t = 0; t < 2; ++t) {
                     mbar_wait(&q_full[t], item_par);
                     tc_fence_after();
-                    issue_S(t, slot_of(0));
-                    umma_commit(&s_full[t]);
-                    if (it.n[t] == 1) umma_commit(&q_empty[t]);
+                    if (elect_one()) {
+                        issue_S(t, slot_of(0));
+                        umma_commit(&s_full[t]);
+                        if ((t ? n1 : n0) == 1) umma_commit(&q_empty[t]);
+                        if (t == 1) umma_commit(&kv_empty[slot_of(0)]);
+                    }
+                    __syncwarp();
                 }
-                umma_commit(&kv_empty[slot_of(0)]);
-                for (int j = 0; j < n_max; ++j) {
+                for (int j = 0; j < n1; ++j) {
 #pragma unroll 1
                     for (int t = 0; t < 2; ++t) {
-                        if (j >= it.n[t]) continue;
+                        const int nt = t ? n1 : n0;
+                        if (j >= nt) continue;
                         // ---- O_t += P_t(j) V_j ----
                         wait_kv(2 * j + 1);
                         if (j == 0) {
@@ -375,22 +382,25 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                         mbar_wait(&p_full[t], (p_par >> t) & 1);
                         p_par ^= 1u << t;
+                        const bool more = j + 1 < nt;
+                        if (more) wait_kv(2 * j + 2);
                         tc_fence_after();
-                        issue_PV(t, slot_of(2 * j + 1), j > 0 ? 1u : 0u);
-                        if (j == it.n[t] - 1) umma_commit(&o_final[t]);
-                        if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 1)]);
-                        // ---- S_t(j+1) = Q_t K_{j+1}^T ----
-                        if (j + 1 < it.n[t]) {
-                            wait_kv(2 * j + 2);
-                            tc_fence_after();
-                            issue_S(t, slot_of(2 * j + 2));
-                            umma_commit(&s_full[t]);
-                            if (j + 2 == it.n[t]) umma_commit(&q_empty[t]);
+                        if (elect_one()) {
+                            issue_PV(t, slot_of(2 * j + 1), j > 0 ? 1u : 0u);
+                            if (!more) umma_commit(&o_final[t]);
+                            if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 1)]);
+                            // ---- S_t(j+1) = Q_t K_{j+1}^T ----
+                            if (more) {
+                                issue_S(t, slot_of(2 * j + 2));
+                                umma_commit(&s_full[t]);
+                                if (j + 2 == nt) umma_commit(&q_empty[t]);
+                                if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 2)]);
+                            }
                         }
-                        if (t == 1 && j + 1 < n_max) umma_commit(&kv_empty[slot_of(2 * j + 2)]);
+                        __syncwarp();
                     }
                 }
-                kv_cnt += 2 * n_max;
+                kv_cnt += 2 * n1;
             }
         } else if (warp == 13 && lane == 0) {
             // =========================== TMA producer ===========================
