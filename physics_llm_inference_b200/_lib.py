@@ -10,7 +10,8 @@ import os
 import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libpli_attention.so")
+# PLI_LIB_PATH: load another build of the same ABI (kernel tuning experiments); never a fallback
+LIB_PATH = os.environ.get("PLI_LIB_PATH") or os.path.join(_PKG, "libpli_attention.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "pli_attention.h")
 
 PLI_BF16, PLI_F16, PLI_F32 = 0, 1, 2
@@ -45,6 +46,7 @@ _SIGNATURES = {
                                    _I64P, C.c_int, _VP]),
     # debug aid, not declared in the public header
     "pli_debug_umma_selftest": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
+    "pli_debug_prefill_trace": (C.c_int, [_VP, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -46,8 +46,8 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(nvcc: str, src: str, obj: str, verbose: bool) -> str:
-    cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+def _compile(nvcc: str, src: str, obj: str, verbose: bool, defines=()) -> str:
+    cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -59,27 +59,37 @@ def _compile(nvcc: str, src: str, obj: str, verbose: bool) -> str:
     return log
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines=()) -> str:
+    """Build the library.  `variant` + `defines` produce a tuning build next to the product one
+    (build/libpli_attention_<variant>.so, e.g. -DPLI_PROFILE=1 or -DPLI_POLY_PAIRS=6); the product
+    library is always the default, define-free build."""
     nvcc = find_nvcc()
     os.makedirs(OBJ, exist_ok=True)
     jobs = []
     objs = []
+    suffix = f"_{variant}" if variant else ""
+    lib = os.path.join(OBJ, f"libpli_attention{suffix}.so") if variant else LIB
     for name in SOURCES:
         src = os.path.join(CSRC, name)
-        obj = os.path.join(OBJ, name.replace(".cu", ".o"))
+        obj = os.path.join(OBJ, name.replace(".cu", f"{suffix}.o"))
         objs.append(obj)
         if force or _stale(obj, [src, *HEADERS]):
             jobs.append((src, obj))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
-            list(ex.map(lambda so: _compile(nvcc, so[0], so[1], verbose), jobs))
-    if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+            list(ex.map(lambda so: _compile(nvcc, so[0], so[1], verbose, tuple(defines)), jobs))
+    if force or jobs or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    variant = ""
+    defines = [a for a in sys.argv[1:] if a.startswith("-D")]
+    for a in sys.argv[1:]:
+        if a.startswith("--variant="):
+            variant = a.split("=", 1)[1]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=variant, defines=defines))

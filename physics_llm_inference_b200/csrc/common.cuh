@@ -318,6 +318,43 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
     return y;
 }
+// packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two lanes per FMA-pipe instruction
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}\n"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// exp2 on the FMA/ALU pipes for a pair of arguments (|relative error| < 8e-5, far below the bf16
+// resolution of P).  x is clamped to >= -126 (so -inf from masking maps to ~1e-38 ~ 0); round-to-nearest
+// split x = n + f with the 1.5*2^23 magic constant, 2^f by a degree-3 minimax polynomial on [-0.5, 0.5],
+// then n is added into the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+    const float kMagic = 12582912.f;
+    x.x = fmaxf(x.x, -126.f);
+    x.y = fmaxf(x.y, -126.f);
+    const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+    const float2 r = fadd2(t, make_float2(-kMagic, -kMagic));
+    const float2 f = fadd2(x, make_float2(-r.x, -r.y));
+    float2 p = ffma2(make_float2(0.0551716573536396f, 0.0551716573536396f), f,
+                     make_float2(0.2426111251115799f, 0.2426111251115799f));
+    p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+    p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+    float2 out;
+    out.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+    out.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+    return out;
+}
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     uint32_t r;

@@ -30,6 +30,14 @@ constexpr int kBN = 128;               // keys per KV tile
 constexpr int kThreads = 512;
 constexpr int kSubTileBytes = 128 * 128;  // [128 rows][64 el] bf16
 constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale O only when the max grew by more
+#ifndef PLI_POLY_PAIRS
+#define PLI_POLY_PAIRS 0
+#endif
+constexpr int kPolyPairs = PLI_POLY_PAIRS;
+#ifndef PLI_PROFILE
+#define PLI_PROFILE 0                     // 1: compile the in-kernel timeline / phase counters (tuning builds only)
+#endif
+constexpr bool kProfile = PLI_PROFILE != 0;  // of every 16 element pairs, how many take the polynomial exp2
 
 // named barrier ids (0 is __syncthreads)
 constexpr int kBarEpilogue = 1;
@@ -45,7 +53,7 @@ struct SmemLayout {
     static constexpr int kSumOff = kScaleOff + 2 * 128 * 4;        // float [2][128]
     static constexpr int kMaxOff = kSumOff + 2 * 128 * 4;          // float [2][128]
     static constexpr int kBarOff = kMaxOff + 2 * 128 * 4;
-    static constexpr int kNumBars = 4 + 2 * kKVStages + 14;
+    static constexpr int kNumBars = 4 + 2 * kKVStages + 10;
     static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kTmemPtrOff + 16;
 };
@@ -58,7 +66,25 @@ struct PrefillParams {
     int causal;
     float scale_log2;     // scale * log2(e)
     float scale;
+    // debug aids (pli_debug_prefill_trace): both null / 0 in normal use
+    unsigned long long* trace;   // [0] = record count, then (tag, clock) pairs written by CTA 0
+    int trace_cap;
+    int debug_flags;             // bit 0: skip the exp2 / P computation (timing experiments only)
 };
+
+// CTA 0 timeline: each tracing warp owns region `region` of the buffer and keeps its own cursor in a
+// register (no atomics, stores are fire-and-forget); tag = event | tile << 8 | step << 16; SM-local clock.
+__device__ __forceinline__ void trace_event(const PrefillParams& p, int lane, int region, int& cursor, int event, int t,
+                                            int j) {
+    if (kProfile && p.trace != nullptr && blockIdx.x == 0 && lane == 0) {
+        if (cursor < p.trace_cap) {
+            unsigned long long* dst = p.trace + ((size_t)region * p.trace_cap + cursor) * 2;
+            dst[0] = (unsigned long long)(event | (t << 8) | (j << 16)) | (1ull << 40);
+            dst[1] = clock64();
+        }
+        ++cursor;
+    }
+}
 
 __device__ __forceinline__ int kv_tiles_for(int q0_tile, const PrefillParams& p) {
     // number of KV tiles a Q tile starting at row q0_tile attends to (>= 1)
@@ -115,12 +141,14 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint64_t* kv_full = bars + 4;             // [kStages]
     uint64_t* kv_empty = kv_full + kStages;   // [kStages]
     uint64_t* s_full = kv_empty + kStages;    // [2]   MMA (commit) -> softmax
-    uint64_t* p_full = s_full + 2;            // [2]   softmax (128) -> MMA
-    uint64_t* sc_full = p_full + 2;           // [2]   softmax (128) -> correction: scale factor posted
-    uint64_t* corr_done = sc_full + 2;        // [2]   correction (128) -> MMA: O rescaled
-    uint64_t* o_final = corr_done + 2;        // [2]   MMA (commit) -> correction: last PV done
-    uint64_t* stats_full = o_final + 2;       // [2]   softmax (128) -> correction: row sum / max posted
-    uint64_t* o_free = stats_full + 2;        // [2]   correction (128) -> MMA: O_t read out of TMEM
+    // pv_ok[t]: PV_t(j) may be issued.  Eight arrivals per tile-step: the four softmax warps once P_t(j) is
+    // in TMEM, and the four correction warps once O_t can be accumulated into (rescaled for j >= 1; for
+    // j == 0 drained by the previous item's epilogue, or free at kernel start).  One wait for the MMA warp
+    // instead of three: every satisfied wait costs it ~200 cycles of tensor-pipe idle time.
+    uint64_t* pv_ok = s_full + 2;             // [2]   softmax (4) + correction (4) -> MMA
+    uint64_t* sc_full = pv_ok + 2;            // [2]   softmax (4 warps) -> correction: scale factor posted
+    uint64_t* o_final = sc_full + 2;          // [2]   MMA (commit) -> correction: last PV done
+    uint64_t* stats_full = o_final + 2;       // [2]   softmax (4 warps) -> correction: row sum / max posted
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -130,12 +158,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1);
-            mbar_init(&p_full[i], 128);
-            mbar_init(&sc_full[i], 128);
-            mbar_init(&corr_done[i], 128);
+            mbar_init(&pv_ok[i], 8);           // four softmax warps + four correction warps
+            mbar_init(&sc_full[i], 4);
             mbar_init(&o_final[i], 1);
-            mbar_init(&stats_full[i], 128);
-            mbar_init(&o_free[i], 128);
+            mbar_init(&stats_full[i], 4);
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&kv_full[i], 1);
@@ -156,6 +182,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 
     if (warp < 8) {
         // =========================== softmax warpgroups ===========================
+        // Warpgroup t owns Q tile t; one thread per row (no cross-thread reductions).
         reg_alloc<176>();
         const int t = warp >> 2;                          // Q tile of this warpgroup
         const int row = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
@@ -163,21 +190,29 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint32_t s_addr = tmem_S[t] + lane_addr;
         const float c = p.scale_log2;
         const int off = p.Nk - p.Nq;
-        uint32_t step = 0, item_cnt = 0;
-        for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_cnt) {
+        uint32_t step = 0;
+        int trace_cur = 0;
+        const bool prof = kProfile && p.trace != nullptr && blockIdx.x == 0;
+        long long ph[6] = {0, 0, 0, 0, 0, 0};             // wait S, ld, max, exp+store, post, steps
+        long long tp = 0;
+        for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
             const WorkItem it = decode_item(w, p);
             const int q_row = it.q0 + t * kBM + row;
             float m_ref = -INFINITY;                      // reference max (raw score units)
             float d = 0.f;                                // running row sum relative to m_ref
             for (int j = 0; j < it.n[t]; ++j, ++step) {
+                if (prof) tp = clock64();
                 mbar_wait(&s_full[t], step & 1);
                 tc_fence_after();
+                if (prof) { const long long now = clock64(); ph[0] += now - tp; tp = now; }
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 1, t, j);       // S ready
                 float s[128];
                 tmem_ld_x32(s_addr + 0, s + 0);
                 tmem_ld_x32(s_addr + 32, s + 32);
                 tmem_ld_x32(s_addr + 64, s + 64);
                 tmem_ld_x32(s_addr + 96, s + 96);
                 tc_wait_ld();
+                if (prof) { const long long now = clock64(); ph[1] += now - tp; tp = now; }
                 // mask: key padding and the causal diagonal (warp-uniform test, per-row limit)
                 const int k0 = j * kBN;
                 const bool need_mask = (k0 + kBN > p.Nk) || (p.causal && (k0 + kBN - 1 > it.q0 + t * kBM + off));
@@ -196,6 +231,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     mx3 = fmaxf(mx3, s[i + 3]);
                 }
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 2, t, j);       // row max done
+                if (prof) { const long long now = clock64(); ph[2] += now - tp; tp = now; }
                 float alpha = 1.f;
                 if (j == 0) {
                     m_ref = m_new;                        // first tile: nothing accumulated yet
@@ -206,31 +243,61 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 if (j > 0) {
                     sScale[t * 128 + row] = alpha;
-                    mbar_arrive(&sc_full[t]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sc_full[t]);
                 }
-                const float neg_mc = -m_ref * c;
-                float sum0 = 0.f, sum1 = 0.f;
+                // P = exp2(S*c - m*c): packed FFMA2 for the argument, MUFU.EX2 for most elements and a
+                // degree-3 polynomial on the FMA pipe for kPolyPairs of every 16 pairs (the SFU, at 16
+                // exp2/clk/SM, is as scarce as the tensor pipe here); row sums in packed FADD2 chains.
+                const float2 c2 = make_float2(c, c);
+                const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+                if (kProfile && (p.debug_flags & 1)) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) pk[i] = __float_as_uint(s[ch * 32 + 2 * i]);
+                        tmem_st_x16(s_addr + ch * 16, pk);
+                    }
+                    acc0.x = 1.f;
+                } else
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        const float p0 = ex2_approx(fmaf(s[ch * 32 + 2 * i], c, neg_mc));
-                        const float p1 = ex2_approx(fmaf(s[ch * 32 + 2 * i + 1], c, neg_mc));
-                        sum0 += p0;
-                        sum1 += p1;
-                        pk[i] = pack2<kBf16>(p0, p1);
+                        float2 x = ffma2(make_float2(s[ch * 32 + 2 * i], s[ch * 32 + 2 * i + 1]), c2, nmc2);
+                        float2 pv;
+                        if (i < kPolyPairs) {
+                            pv = exp2_poly2(x);
+                        } else {
+                            pv.x = ex2_approx(x.x);
+                            pv.y = ex2_approx(x.y);
+                        }
+                        if (i & 1) acc1 = fadd2(acc1, pv); else acc0 = fadd2(acc0, pv);
+                        pk[i] = pack2<kBf16>(pv.x, pv.y);
                     }
                     tmem_st_x16(s_addr + ch * 16, pk);    // P aliases S columns [0,64)
                 }
-                d += sum0 + sum1;
+                acc0 = fadd2(acc0, acc1);
+                d += acc0.x + acc0.y;
+                if (prof) { const long long now = clock64(); ph[3] += now - tp; tp = now; }
                 tc_wait_st();
                 tc_fence_before();
-                mbar_arrive(&p_full[t]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pv_ok[t]);
+                if (prof) { const long long now = clock64(); ph[4] += now - tp; tp = now; ph[5] += 1; }
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 3, t, j);       // P posted
             }
             sSum[t * 128 + row] = d;
             sMax[t * 128 + row] = m_ref * c;              // log2 units
-            mbar_arrive(&stats_full[t]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&stats_full[t]);
+        }
+        if (prof && lane == 0 && (warp & 3) == 0) {           // per-phase cycle totals: region 3 of the trace buffer
+            unsigned long long* dst = p.trace + ((size_t)3 * p.trace_cap) * 2 + t * 8;
+            for (int i = 0; i < 6; ++i) dst[i] = (unsigned long long)ph[i];
         }
     } else if (warp < 12) {
         // =========================== correction + epilogue warpgroup ===========================
@@ -239,6 +306,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         uint32_t corr_cnt[2] = {0, 0}, item_cnt = 0;
+        if (lane == 0) {                                  // first item: O_0 / O_1 are free
+            mbar_arrive(&pv_ok[0]);
+            mbar_arrive(&pv_ok[1]);
+        }
         for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_cnt) {
             const WorkItem it = decode_item(w, p);
             for (int j = 1; j < it.n[1]; ++j) {
@@ -262,7 +333,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         tc_wait_st();
                         tc_fence_before();
                     }
-                    mbar_arrive(&corr_done[t]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&pv_ok[t]);
                 }
             }
             // ---- epilogue: O_t / d -> bf16 -> swizzled smem -> TMA store; LSE ----
@@ -288,7 +360,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         tc_wait_ld();
                         if (ch == kD / 32 - 1) {
                             tc_fence_before();
-                            mbar_arrive(&o_free[t]);              // O_t is in registers: TMEM columns reusable
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&pv_ok[t]);    // O_t is in registers: next item's PV_t(0) may overwrite it
                         }
                         uint8_t* srow = sO + row * 128;
 #pragma unroll
@@ -328,7 +401,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const uint32_t k_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboK;
             const uint32_t v_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboV;
             uint32_t kv_cnt = 0, item_par = 0;
-            uint32_t p_par = 0, c_par = 0;                        // bit t: phase parity of p_full[t] / corr_done[t]
+            uint32_t p_par = 0;                                   // bit t: phase parity of pv_ok[t]
+            int trace_cur = 0;
             auto issue_S = [&](int t, uint32_t kslot) {
                 // S_t = Q_t K^T : K-major operands, 16 elements (32 bytes) of head_dim per instruction
                 const uint32_t qa = q_lo + t * (kTileBytes >> 4), ka = k_lo + kslot * (kTileBytes >> 4);
@@ -368,36 +442,31 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     __syncwarp();
                 }
                 for (int j = 0; j < n1; ++j) {
+                    // K/V of this step: normally landed long ago (the ring runs ~1.5 steps ahead)
+                    wait_kv(2 * j + 1);
+                    if (j + 1 < n1) wait_kv(2 * j + 2);
 #pragma unroll 1
                     for (int t = 0; t < 2; ++t) {
                         const int nt = t ? n1 : n0;
                         if (j >= nt) continue;
-                        // ---- O_t += P_t(j) V_j ----
-                        wait_kv(2 * j + 1);
-                        if (j == 0) {
-                            mbar_wait(&o_free[t], item_par ^ 1);
-                        } else {
-                            mbar_wait(&corr_done[t], (c_par >> t) & 1);
-                            c_par ^= 1u << t;
-                        }
-                        mbar_wait(&p_full[t], (p_par >> t) & 1);
+                        mbar_wait(&pv_ok[t], (p_par >> t) & 1);
                         p_par ^= 1u << t;
                         const bool more = j + 1 < nt;
-                        if (more) wait_kv(2 * j + 2);
                         tc_fence_after();
+                        trace_event(p, lane, 2, trace_cur, 4, t, j);                        // inputs of PV_t(j) ready
                         if (elect_one()) {
-                            issue_PV(t, slot_of(2 * j + 1), j > 0 ? 1u : 0u);
+                            issue_PV(t, slot_of(2 * j + 1), j > 0 ? 1u : 0u);              // O_t += P_t(j) V_j
                             if (!more) umma_commit(&o_final[t]);
                             if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 1)]);
-                            // ---- S_t(j+1) = Q_t K_{j+1}^T ----
                             if (more) {
-                                issue_S(t, slot_of(2 * j + 2));
+                                issue_S(t, slot_of(2 * j + 2));                          // S_t(j+1) = Q_t K_{j+1}^T
                                 umma_commit(&s_full[t]);
                                 if (j + 2 == nt) umma_commit(&q_empty[t]);
                                 if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 2)]);
                             }
                         }
                         __syncwarp();
+                        trace_event(p, lane, 2, trace_cur, 5, t, j);                        // issued
                     }
                 }
                 kv_cnt += 2 * n1;
@@ -544,6 +613,10 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+unsigned long long* g_trace_buf = nullptr;
+int g_trace_cap = 0;
+int g_debug_flags = 0;
+
 int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int H, int B, const int64_t* st) {
     EncodeTiledFn enc = get_encode_tiled();
     if (enc == nullptr) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -600,6 +673,9 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     p.causal = causal;
     p.scale = scale;
     p.scale_log2 = scale * kLog2e;
+    p.trace = g_trace_buf;
+    p.trace_cap = g_trace_cap;
+    p.debug_flags = g_debug_flags;
     const bool bf16 = dtype == PLI_BF16;
     if (D == 128) return bf16 ? launch_t<128, true>(mq, mk, mv, mo, p, stream) : launch_t<128, false>(mq, mk, mv, mo, p, stream);
     return bf16 ? launch_t<64, true>(mq, mk, mv, mo, p, stream) : launch_t<64, false>(mq, mk, mv, mo, p, stream);
@@ -608,6 +684,15 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
 }  // namespace pli
 
 using namespace pli;
+
+// Debug aid: record CTA 0's pipeline timeline of the next prefill launches into `buf` (device memory of
+// 3 regions x capacity x 16 bytes, zeroed by the caller); buf = NULL switches it off.  flags bit 0 skips exp2.
+extern "C" int pli_debug_prefill_trace(void* buf, int capacity, int flags) {
+    g_trace_buf = static_cast<unsigned long long*>(buf);
+    g_trace_cap = buf ? capacity : 0;
+    g_debug_flags = flags;
+    return PLI_OK;
+}
 
 // Debug aid (not part of the reference-facing surface): a (128 x D), b (128 x D), c (128 x D) row-major
 // device tensors; s_out (128 x 128) f32 = a b^T; o_out (128 x D) f32 = cast(s_out / 64) c.
