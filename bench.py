@@ -52,6 +52,17 @@ def load_peaks():
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def load_traffic(key: str):
+    """DRAM bytes per launch of the named kernel from the committed ncu capture (profiles/ncu_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)[key]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def config_dict(n_gpus: int):
     return {"workload": "C2: causal GQA prefill, 32q/8kv heads, D128, N8192, batch 4 per GPU, bf16",
             "global_batch": C2["B"] * n_gpus, "seq_len": C2["N"], "heads": f"{C2['Hq']}q/{C2['Hkv']}kv",
@@ -163,6 +174,8 @@ def run_reference(args, rank: int):
     if rank != 0:
         return
     import torch
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     s = CPU_SAMPLE
     for _ in range(min(args.warmup, 1)):
         cpu_prefill_sample()
@@ -319,7 +332,8 @@ def main():
                              "l2_policy": "three 1 GiB K/V pool pairs rotated (each larger than L2)"},
                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
-                               "frac_of_8tbs": gbs / 8000.0, "traffic": None,
+                               "frac_of_8tbs": gbs / 8000.0, "traffic": load_traffic("decode_tma_kernel<128,bf16> C3"),
+                               "algorithmic_bytes": nbytes,
                                "note": "split-KV kernel + combine kernel timed together; algorithmic bytes = K,V once + q,o + table"}}
         del pools
 
@@ -342,7 +356,9 @@ def main():
                      "frac": value / world / peaks["bf16_tflops"],
                      "peak_source": peaks["source"] + " cuBLAS bf16 burst (kernel timed alone, back to back)",
                      "frac_of_sustained": (value / world / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
-                     "frac_of_datasheet_2250": value / world / 2250.0, "traffic": None,
+                     "frac_of_datasheet_2250": value / world / 2250.0,
+                     "traffic": load_traffic("prefill_tcgen05_kernel<128,bf16> C2"),
+                     "algorithmic_bytes": 4 * C2["B"] * C2["N"] * C2["D"] * (C2["Hq"] + C2["Hkv"]),
                      "kernel": "prefill_tcgen05_kernel<128,bf16>", "flops_per_launch": flops_step},
     }
     if decode is not None:
