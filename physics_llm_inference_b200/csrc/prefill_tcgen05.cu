@@ -31,7 +31,7 @@ constexpr int kThreads = 512;
 constexpr int kSubTileBytes = 128 * 128;  // [128 rows][64 el] bf16
 constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale O only when the max grew by more
 #ifndef PLI_POLY_PAIRS
-#define PLI_POLY_PAIRS 0
+#define PLI_POLY_PAIRS 4
 #endif
 constexpr int kPolyPairs = PLI_POLY_PAIRS;
 #ifndef PLI_PROFILE
@@ -49,11 +49,11 @@ struct SmemLayout {
     static constexpr int kQOff = 0;
     static constexpr int kKVOff = 2 * kTileBytes;
     static constexpr int kOOff = kKVOff + kKVStages * kTileBytes;  // one [128 x 64] staging sub-tile
-    static constexpr int kScaleOff = kOOff + kSubTileBytes;        // float [2][128]
-    static constexpr int kSumOff = kScaleOff + 2 * 128 * 4;        // float [2][128]
+    static constexpr int kScaleOff = kOOff + kSubTileBytes;        // float [2 tiles][2 buffers][128]
+    static constexpr int kSumOff = kScaleOff + 4 * 128 * 4;        // float [2][128]
     static constexpr int kMaxOff = kSumOff + 2 * 128 * 4;          // float [2][128]
     static constexpr int kBarOff = kMaxOff + 2 * 128 * 4;
-    static constexpr int kNumBars = 4 + 2 * kKVStages + 10;
+    static constexpr int kNumBars = 4 + 2 * kKVStages + 16;
     static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kTmemPtrOff + 16;
 };
@@ -86,18 +86,30 @@ __device__ __forceinline__ void trace_event(const PrefillParams& p, int lane, in
     }
 }
 
-__device__ __forceinline__ int kv_tiles_for(int q0_tile, const PrefillParams& p) {
-    // number of KV tiles a Q tile starting at row q0_tile attends to (>= 1)
+constexpr int kHN = 64;                // keys per softmax / MMA half-step (half of a KV tile)
+
+__device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& p) {
+    // number of 64-key half-steps a Q tile starting at row q0_tile attends to (>= 1)
     int kmax = p.Nk;
     if (p.causal) kmax = min(p.Nk, q0_tile + kBM + (p.Nk - p.Nq));
     kmax = max(kmax, 1);
-    return (kmax + kBN - 1) / kBN;
+    return (kmax + kHN - 1) / kHN;
 }
 
 struct WorkItem {
     int b, h, hk, q0;     // q0 = first row of Q tile 0; tile 1 starts at q0 + 128
-    int n[2];             // KV tiles per Q tile
+    int n[2];             // 64-key half-steps per Q tile (n[1] >= n[0])
+    int n_kv;             // 128-key K/V tiles to load
 };
+
+// Static persistent schedule, longest item first.  Round i hands items [i*G, (i+1)*G) to the G CTAs, in
+// forward order on even rounds and reversed on odd rounds ("snake"), which cancels the within-round size
+// gradient: C2 load imbalance 0.3 % instead of 3.4 % for plain round-robin.  Returns -1 when the CTA is done.
+__device__ __forceinline__ int item_of_round(int i, const PrefillParams& p) {
+    const int G = (int)gridDim.x, c = (int)blockIdx.x;
+    const long long w = (long long)i * G + ((i & 1) ? G - 1 - c : c);
+    return w < p.total_items ? (int)w : -1;
+}
 
 __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
     // longest first: pair index descends as w grows; q heads of a KV group are adjacent in w
@@ -109,9 +121,10 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
     it.h = r % p.Hq;
     it.hk = it.h / (p.Hq / p.Hkv);
     it.q0 = pair * 2 * kBM;
-    it.n[0] = kv_tiles_for(it.q0, p);
-    it.n[1] = kv_tiles_for(it.q0 + kBM, p);
+    it.n[0] = half_steps_for(it.q0, p);
+    it.n[1] = half_steps_for(it.q0 + kBM, p);
     if (it.n[1] < it.n[0]) it.n[1] = it.n[0];
+    it.n_kv = (it.n[1] + 1) >> 1;
     return it;
 }
 
@@ -124,7 +137,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     constexpr int kStages = L::kKVStages;
     constexpr int kTileBytes = L::kTileBytes;
     constexpr int kHalves = kD / 64;
-    constexpr uint32_t kIdescS = make_idesc_f16(kBM, kBN, kBf16, false, false);  // Q K^T: both K-major
+    constexpr uint32_t kIdescS = make_idesc_f16(kBM, kHN, kBf16, false, false);  // Q K^T (64 keys): both K-major
     constexpr uint32_t kIdescO = make_idesc_f16(kBM, kD, kBf16, false, true);    // P V: B (V) is MN-major
 
     extern __shared__ uint8_t smem_raw[];
@@ -132,23 +145,23 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint8_t* sQ = smem + L::kQOff;
     uint8_t* sKV = smem + L::kKVOff;
     uint8_t* sO = smem + L::kOOff;
-    float* sScale = reinterpret_cast<float*>(smem + L::kScaleOff);
-    float* sSum = reinterpret_cast<float*>(smem + L::kSumOff);
-    float* sMax = reinterpret_cast<float*>(smem + L::kMaxOff);
+    float* sScale = reinterpret_cast<float*>(smem + L::kScaleOff);   // [2 tiles][2 buffers][128]
+    float* sSum = reinterpret_cast<float*>(smem + L::kSumOff);       // [2][128]
+    float* sMax = reinterpret_cast<float*>(smem + L::kMaxOff);       // [2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-    uint64_t* q_full = bars;                  // [2]   TMA -> MMA
-    uint64_t* q_empty = bars + 2;             // [2]   MMA (commit) -> TMA
-    uint64_t* kv_full = bars + 4;             // [kStages]
-    uint64_t* kv_empty = kv_full + kStages;   // [kStages]
-    uint64_t* s_full = kv_empty + kStages;    // [2]   MMA (commit) -> softmax
-    // pv_ok[t]: PV_t(j) may be issued.  Eight arrivals per tile-step: the four softmax warps once P_t(j) is
-    // in TMEM, and the four correction warps once O_t can be accumulated into (rescaled for j >= 1; for
-    // j == 0 drained by the previous item's epilogue, or free at kernel start).  One wait for the MMA warp
-    // instead of three: every satisfied wait costs it ~200 cycles of tensor-pipe idle time.
-    uint64_t* pv_ok = s_full + 2;             // [2]   softmax (4) + correction (4) -> MMA
-    uint64_t* sc_full = pv_ok + 2;            // [2]   softmax (4 warps) -> correction: scale factor posted
-    uint64_t* o_final = sc_full + 2;          // [2]   MMA (commit) -> correction: last PV done
-    uint64_t* stats_full = o_final + 2;       // [2]   softmax (4 warps) -> correction: row sum / max posted
+    uint64_t* q_full = bars;                  // [2]      TMA -> MMA warp t
+    uint64_t* q_empty = bars + 2;             // [2]      MMA warp t (commit) -> TMA
+    uint64_t* kv_full = bars + 4;             // [kStages] TMA -> both MMA warps
+    uint64_t* kv_empty = kv_full + kStages;   // [kStages] both MMA warps (commit, count 2) -> TMA
+    // Index [t * 2 + h]: Q tile t, S/P buffer h (= half-step parity).  Each barrier has at most one phase
+    // in flight, which is what lets S run two half-steps ahead of the softmax.
+    uint64_t* s_full = kv_empty + kStages;    // [4]  MMA (commit) -> softmax: S_t(s) is in buffer h
+    // pv_ok: PV_t(s) may be issued: four softmax-warp arrivals (P_t(s) written over S in buffer h) + four
+    // correction-warp arrivals (O_t rescaled for s >= 1; drained by the previous item / free at start for s == 0).
+    uint64_t* pv_ok = s_full + 4;             // [4]
+    uint64_t* sc_full = pv_ok + 4;            // [4]  softmax (4 warps) -> correction: scale factor of step s posted
+    uint64_t* o_final = sc_full + 4;          // [2]  MMA (commit) -> correction: last PV of the item done
+    uint64_t* stats_full = o_final + 2;       // [2]  softmax (4 warps) -> correction: row sum / max posted
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -157,15 +170,17 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         for (int i = 0; i < 2; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1);
-            mbar_init(&s_full[i], 1);
-            mbar_init(&pv_ok[i], 8);           // four softmax warps + four correction warps
-            mbar_init(&sc_full[i], 4);
             mbar_init(&o_final[i], 1);
             mbar_init(&stats_full[i], 4);
         }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&pv_ok[i], 8);
+            mbar_init(&sc_full[i], 4);
+        }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 1);
+            mbar_init(&kv_empty[i], 2);
         }
         fence_barrier_init();
     }
@@ -177,97 +192,80 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const uint32_t tmem_S[2] = {tmem_base, tmem_base + 128};
-    const uint32_t tmem_O[2] = {tmem_base + 256, tmem_base + 384};
+    // TMEM: S_t buffer h at column t*128 + h*64 (P aliases its first 32 columns); O_t at 256 + t*128.
 
     if (warp < 8) {
         // =========================== softmax warpgroups ===========================
-        // Warpgroup t owns Q tile t; one thread per row (no cross-thread reductions).
+        // Warpgroup t owns Q tile t; one thread per row (no cross-thread reductions).  Half-step s handles
+        // keys [64 s, 64 s + 64) out of S buffer s & 1.
         reg_alloc<176>();
-        const int t = warp >> 2;                          // Q tile of this warpgroup
+        const int t = warp >> 2;
         const int row = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t s_addr = tmem_S[t] + lane_addr;
         const float c = p.scale_log2;
         const int off = p.Nk - p.Nq;
-        uint32_t step = 0;
+        uint32_t sf_par = 0;                              // bit h: phase parity of s_full[t*2+h]
         int trace_cur = 0;
-        const bool prof = kProfile && p.trace != nullptr && blockIdx.x == 0;
-        long long ph[6] = {0, 0, 0, 0, 0, 0};             // wait S, ld, max, exp+store, post, steps
-        long long tp = 0;
-        for (int w = blockIdx.x; w < p.total_items; w += gridDim.x) {
+        for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd) {
             const WorkItem it = decode_item(w, p);
-            const int q_row = it.q0 + t * kBM + row;
+            const int q_tile0 = it.q0 + t * kBM;
+            const int q_row = q_tile0 + row;
+            const int nt = it.n[t];
             float m_ref = -INFINITY;                      // reference max (raw score units)
             float d = 0.f;                                // running row sum relative to m_ref
-            for (int j = 0; j < it.n[t]; ++j, ++step) {
-                if (prof) tp = clock64();
-                mbar_wait(&s_full[t], step & 1);
+            for (int s = 0; s < nt; ++s) {
+                const int h = s & 1;
+                const uint32_t s_addr = tmem_base + t * 128 + h * 64 + lane_addr;
+                mbar_wait(&s_full[t * 2 + h], (sf_par >> h) & 1);
+                sf_par ^= 1u << h;
                 tc_fence_after();
-                if (prof) { const long long now = clock64(); ph[0] += now - tp; tp = now; }
-                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 1, t, j);       // S ready
-                float s[128];
-                tmem_ld_x32(s_addr + 0, s + 0);
-                tmem_ld_x32(s_addr + 32, s + 32);
-                tmem_ld_x32(s_addr + 64, s + 64);
-                tmem_ld_x32(s_addr + 96, s + 96);
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 1, t, s);       // S ready
+                float sv[64];
+                tmem_ld_x32(s_addr + 0, sv + 0);
+                tmem_ld_x32(s_addr + 32, sv + 32);
                 tc_wait_ld();
-                if (prof) { const long long now = clock64(); ph[1] += now - tp; tp = now; }
                 // mask: key padding and the causal diagonal (warp-uniform test, per-row limit)
-                const int k0 = j * kBN;
-                const bool need_mask = (k0 + kBN > p.Nk) || (p.causal && (k0 + kBN - 1 > it.q0 + t * kBM + off));
+                const int k0 = s * kHN;
+                const bool need_mask = (k0 + kHN > p.Nk) || (p.causal && (k0 + kHN - 1 > q_tile0 + off));
                 if (need_mask) {
                     int vis = p.Nk - 1 - k0;
                     if (p.causal) vis = min(vis, q_row + off - k0);
 #pragma unroll
-                    for (int i = 0; i < 128; ++i) s[i] = (i <= vis) ? s[i] : -INFINITY;
+                    for (int i = 0; i < 64; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
                 }
-                float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+                float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
-                for (int i = 4; i < 128; i += 4) {
-                    mx0 = fmaxf(mx0, s[i]);
-                    mx1 = fmaxf(mx1, s[i + 1]);
-                    mx2 = fmaxf(mx2, s[i + 2]);
-                    mx3 = fmaxf(mx3, s[i + 3]);
+                for (int i = 4; i < 64; i += 4) {
+                    mx0 = fmaxf(mx0, sv[i]);
+                    mx1 = fmaxf(mx1, sv[i + 1]);
+                    mx2 = fmaxf(mx2, sv[i + 2]);
+                    mx3 = fmaxf(mx3, sv[i + 3]);
                 }
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
-                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 2, t, j);       // row max done
-                if (prof) { const long long now = clock64(); ph[2] += now - tp; tp = now; }
                 float alpha = 1.f;
-                if (j == 0) {
-                    m_ref = m_new;                        // first tile: nothing accumulated yet
+                if (s == 0) {
+                    m_ref = m_new;                        // first half-step: nothing accumulated yet
                 } else if ((m_new - m_ref) * c > kRescaleThreshold) {
                     alpha = ex2_approx((m_ref - m_new) * c);
                     m_ref = m_new;
                     d *= alpha;
                 }
-                if (j > 0) {
-                    sScale[t * 128 + row] = alpha;
+                if (s > 0) {
+                    sScale[(t * 2 + h) * 128 + row] = alpha;
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sc_full[t]);
+                    if (lane == 0) mbar_arrive(&sc_full[t * 2 + h]);
                 }
-                // P = exp2(S*c - m*c): packed FFMA2 for the argument, MUFU.EX2 for most elements and a
-                // degree-3 polynomial on the FMA pipe for kPolyPairs of every 16 pairs (the SFU, at 16
-                // exp2/clk/SM, is as scarce as the tensor pipe here); row sums in packed FADD2 chains.
+                // P = exp2(S*c - m*c): packed FFMA2 for the argument, MUFU.EX2 (optionally an FMA-pipe polynomial
+                // for kPolyPairs of every 16 pairs), row sums in packed FADD2 chains.
                 const float2 c2 = make_float2(c, c);
                 const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-                if (kProfile && (p.debug_flags & 1)) {
 #pragma unroll
-                    for (int ch = 0; ch < 4; ++ch) {
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) pk[i] = __float_as_uint(s[ch * 32 + 2 * i]);
-                        tmem_st_x16(s_addr + ch * 16, pk);
-                    }
-                    acc0.x = 1.f;
-                } else
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < 2; ++ch) {
                     uint32_t pk[16];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
-                        float2 x = ffma2(make_float2(s[ch * 32 + 2 * i], s[ch * 32 + 2 * i + 1]), c2, nmc2);
+                        float2 x = ffma2(make_float2(sv[ch * 32 + 2 * i], sv[ch * 32 + 2 * i + 1]), c2, nmc2);
                         float2 pv;
                         if (i < kPolyPairs) {
                             pv = exp2_poly2(x);
@@ -278,26 +276,20 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         if (i & 1) acc1 = fadd2(acc1, pv); else acc0 = fadd2(acc0, pv);
                         pk[i] = pack2<kBf16>(pv.x, pv.y);
                     }
-                    tmem_st_x16(s_addr + ch * 16, pk);    // P aliases S columns [0,64)
+                    tmem_st_x16(s_addr + ch * 16, pk);    // P aliases the first 32 columns of its S buffer
                 }
                 acc0 = fadd2(acc0, acc1);
                 d += acc0.x + acc0.y;
-                if (prof) { const long long now = clock64(); ph[3] += now - tp; tp = now; }
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&pv_ok[t]);
-                if (prof) { const long long now = clock64(); ph[4] += now - tp; tp = now; ph[5] += 1; }
-                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 3, t, j);       // P posted
+                if (lane == 0) mbar_arrive(&pv_ok[t * 2 + h]);
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 3, t, s);       // P posted
             }
             sSum[t * 128 + row] = d;
             sMax[t * 128 + row] = m_ref * c;              // log2 units
             __syncwarp();
             if (lane == 0) mbar_arrive(&stats_full[t]);
-        }
-        if (prof && lane == 0 && (warp & 3) == 0) {           // per-phase cycle totals: region 3 of the trace buffer
-            unsigned long long* dst = p.trace + ((size_t)3 * p.trace_cap) * 2 + t * 8;
-            for (int i = 0; i < 6; ++i) dst[i] = (unsigned long long)ph[i];
         }
     } else if (warp < 12) {
         // =========================== correction + epilogue warpgroup ===========================
@@ -305,43 +297,45 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        uint32_t corr_cnt[2] = {0, 0}, item_cnt = 0;
+        uint32_t sc_par = 0, item_cnt = 0;                // sc_par bit t*2+h: phase parity of sc_full[t*2+h]
         if (lane == 0) {                                  // first item: O_0 / O_1 are free
             mbar_arrive(&pv_ok[0]);
-            mbar_arrive(&pv_ok[1]);
+            mbar_arrive(&pv_ok[2]);
         }
-        for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, ++item_cnt) {
+        for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, ++item_cnt) {
             const WorkItem it = decode_item(w, p);
-            for (int j = 1; j < it.n[1]; ++j) {
+            for (int s = 1; s < it.n[1]; ++s) {
+                const int h = s & 1;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    if (j >= it.n[t]) continue;
-                    mbar_wait(&sc_full[t], corr_cnt[t] & 1);
-                    ++corr_cnt[t];
-                    const float alpha = sScale[t * 128 + row];
+                    if (s >= it.n[t]) continue;
+                    const int bi = t * 2 + h;
+                    mbar_wait_relaxed(&sc_full[bi], (sc_par >> bi) & 1);
+                    sc_par ^= 1u << bi;
+                    const float alpha = sScale[bi * 128 + row];
                     if (__any_sync(0xffffffffu, alpha != 1.f)) {
                         tc_fence_after();
 #pragma unroll
                         for (int ch = 0; ch < kD / 32; ++ch) {
                             float orr[32];
-                            tmem_ld_x32(tmem_O[t] + lane_addr + ch * 32, orr);
+                            tmem_ld_x32(tmem_base + 256 + t * 128 + lane_addr + ch * 32, orr);
                             tc_wait_ld();
 #pragma unroll
                             for (int i = 0; i < 32; ++i) orr[i] *= alpha;
-                            tmem_st_x32(tmem_O[t] + lane_addr + ch * 32, orr);
+                            tmem_st_x32(tmem_base + 256 + t * 128 + lane_addr + ch * 32, orr);
                         }
                         tc_wait_st();
                         tc_fence_before();
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&pv_ok[t]);
+                    if (lane == 0) mbar_arrive(&pv_ok[bi]);
                 }
             }
             // ---- epilogue: O_t / d -> bf16 -> swizzled smem -> TMA store; LSE ----
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
-                mbar_wait(&stats_full[t], item_cnt & 1);
-                mbar_wait(&o_final[t], item_cnt & 1);
+                mbar_wait_relaxed(&stats_full[t], item_cnt & 1);
+                mbar_wait_relaxed(&o_final[t], item_cnt & 1);
                 tc_fence_after();
                 const float dsum = sSum[t * 128 + row];
                 const float mlog2 = sMax[t * 128 + row];
@@ -356,12 +350,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     for (int c2 = 0; c2 < 2; ++c2) {
                         const int ch = hf * 2 + c2;                   // 32-column chunk of O_t
                         float orr[32];
-                        tmem_ld_x32(tmem_O[t] + lane_addr + ch * 32, orr);
+                        tmem_ld_x32(tmem_base + 256 + t * 128 + lane_addr + ch * 32, orr);
                         tc_wait_ld();
                         if (ch == kD / 32 - 1) {
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&pv_ok[t]);    // O_t is in registers: next item's PV_t(0) may overwrite it
+                            // O_t is in registers: the next item's PV_t(0) (buffer 0) may overwrite it
+                            if (lane == 0) mbar_arrive(&pv_ok[t * 2]);
                         }
                         uint8_t* srow = sO + row * 128;
 #pragma unroll
@@ -389,100 +384,112 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (warp == 8 && lane == 0) tma_store_wait_all<0>();
     } else {
         reg_dealloc<64>();
-        if (warp == 12) {
-            // =========================== MMA issuer ===========================
-            // All 32 lanes run the (warp-uniform) control flow and the waits so the address arithmetic stays
-            // on the uniform datapath; one elected lane issues tcgen05.mma / tcgen05.commit.
-            // Descriptor high word is constant: SBO = 1024 B (8 rows x 128 B), version 1, SWIZZLE_128B.
-            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
-            constexpr uint32_t kLboK = 1u << 16;                           // K-major: LBO unused (1)
+        if (warp == 12 || warp == 13) {
+            // =========================== MMA issuers: warp 12 -> Q tile 0, warp 13 -> Q tile 1 ===========================
+            // tcgen05.mma issue is nearly synchronous (the queue holds ~2 instructions), so each tile gets its own
+            // issuing warp: while one waits on a barrier the other keeps the tensor pipe busy.  All 32 lanes run the
+            // warp-uniform control flow (addresses stay in uniform registers); one elected lane issues.
+            // Per half-step s: O_t += P_t(s) V[64 s .. 64 s + 64), then S_t(s+2) = Q_t K[64 (s+2) ..]^T into the
+            // buffer P_t(s) just vacated, so S always runs two half-steps ahead of the softmax.
+            const int t = warp - 12;
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO 1024 B, version 1, SWIZZLE_128B
+            constexpr uint32_t kLboK = 1u << 16;                              // K-major: LBO unused (1)
             constexpr uint32_t kLboV = (uint32_t)(kSubTileBytes >> 4) << 16;  // MN-major: LBO = one sub-tile
-            const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFFu) | kLboK;
+            const uint32_t q_lo = (((smem_u32(sQ) + t * kTileBytes) >> 4) & 0x3FFFu) | kLboK;
             const uint32_t k_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboK;
             const uint32_t v_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboV;
-            uint32_t kv_cnt = 0, item_par = 0;
-            uint32_t p_par = 0;                                   // bit t: phase parity of pv_ok[t]
+            const uint32_t tmem_s = tmem_base + t * 128, tmem_o = tmem_base + 256 + t * 128;
+            uint32_t kv_cnt = 0, item_par = 0, pv_par = 0;        // pv_par bit h: phase parity of pv_ok[t*2+h]
             int trace_cur = 0;
-            auto issue_S = [&](int t, uint32_t kslot) {
-                // S_t = Q_t K^T : K-major operands, 16 elements (32 bytes) of head_dim per instruction
-                const uint32_t qa = q_lo + t * (kTileBytes >> 4), ka = k_lo + kslot * (kTileBytes >> 4);
+            auto issue_S = [&](int s, uint32_t kslot) {
+                // S_t(s) = Q_t K[rows 64 (s&1) .. +64 of the tile]^T : K-major, 32 bytes of head_dim per MMA
+                const uint32_t ka = k_lo + kslot * (kTileBytes >> 4) + (s & 1) * ((kHN * 128) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks) {
                     const uint32_t koff = ((ks >> 2) * kSubTileBytes + (ks & 3) * 32) >> 4;
-                    umma_ss_lohi(tmem_base + t * 128, qa + koff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
+                    umma_ss_lohi(tmem_s + (s & 1) * 64, q_lo + koff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
                 }
             };
-            auto issue_PV = [&](int t, uint32_t vslot, uint32_t accumulate) {
-                // O_t += P_t V : A = P from TMEM (8 columns per 16 keys), B = V MN-major (16 keys = 2048 B)
-                const uint32_t va = v_lo + vslot * (kTileBytes >> 4);
+            auto issue_PV = [&](int s, uint32_t vslot) {
+                // O_t += P_t(s) V[rows 64 (s&1) .. +64] : A = P from TMEM (8 columns per 16 keys), B = V MN-major
+                const uint32_t va = v_lo + vslot * (kTileBytes >> 4) + (s & 1) * ((kHN * 128) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < kBN / 16; ++ks)
-                    umma_ts_lohi(tmem_base + 256 + t * 128, tmem_base + t * 128 + ks * 8, va + ks * (2048 >> 4), kDescHi,
-                                 kIdescO, ks > 0 ? 1u : accumulate);
+                for (int ks = 0; ks < kHN / 16; ++ks)
+                    umma_ts_lohi(tmem_o, tmem_s + (s & 1) * 64 + ks * 8, va + ks * (2048 >> 4), kDescHi, kIdescO,
+                                 (s > 0 || ks > 0) ? 1u : 0u);
             };
-            for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, item_par ^= 1) {
+            for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
-                const int n0 = it.n[0], n1 = it.n[1];
+                const int nt = it.n[t];
                 auto slot_of = [&](uint32_t idx) -> uint32_t { return (kv_cnt + idx) % kStages; };
                 auto wait_kv = [&](uint32_t idx) {
                     mbar_wait(&kv_full[(kv_cnt + idx) % kStages], ((kv_cnt + idx) / kStages) & 1);
                 };
-                // ---- first S for both tiles ----
+                // K tile j is ring entry 2j, V tile j is ring entry 2j+1.  after_S(s): bookkeeping once S_t(s) is issued
+                auto after_S = [&](int s) {
+                    umma_commit(&s_full[t * 2 + (s & 1)]);
+                    if ((s & 1) || s == nt - 1) umma_commit(&kv_empty[slot_of(2 * (s >> 1))]);   // K tile done (this Q tile)
+                    if (s == nt - 1) umma_commit(&q_empty[t]);
+                };
+                // ---- prologue: S_t(0), S_t(1) from K tile 0 ----
+                mbar_wait(&q_full[t], item_par);
                 wait_kv(0);
-#pragma unroll 1
-                for (int t = 0; t < 2; ++t) {
-                    mbar_wait(&q_full[t], item_par);
+                tc_fence_after();
+                if (elect_one()) {
+                    issue_S(0, slot_of(0));
+                    after_S(0);
+                    if (nt > 1) {
+                        issue_S(1, slot_of(0));
+                        after_S(1);
+                    }
+                }
+                __syncwarp();
+                for (int s = 0; s < nt; ++s) {
+                    const int h = s & 1;
+                    if (h == 0) wait_kv(2 * (s >> 1) + 1);                           // V tile of this pair of half-steps
+                    const bool more = s + 2 < nt;
+                    if (more && h == 0) wait_kv(2 * ((s + 2) >> 1));                 // K tile of the S two half-steps ahead
+                    mbar_wait(&pv_ok[t * 2 + h], (pv_par >> h) & 1);
+                    pv_par ^= 1u << h;
                     tc_fence_after();
+                    trace_event(p, lane, 2 + t, trace_cur, 4, t, s);                        // inputs of PV_t(s) ready
                     if (elect_one()) {
-                        issue_S(t, slot_of(0));
-                        umma_commit(&s_full[t]);
-                        if ((t ? n1 : n0) == 1) umma_commit(&q_empty[t]);
-                        if (t == 1) umma_commit(&kv_empty[slot_of(0)]);
+                        issue_PV(s, slot_of(2 * (s >> 1) + 1));
+                        if (s == nt - 1) umma_commit(&o_final[t]);
+                        if (h || s == nt - 1) umma_commit(&kv_empty[slot_of(2 * (s >> 1) + 1)]);   // V tile done (this Q tile)
+                        if (more) {
+                            issue_S(s + 2, slot_of(2 * ((s + 2) >> 1)));
+                            after_S(s + 2);
+                        }
+                    }
+                    __syncwarp();
+                    trace_event(p, lane, 2 + t, trace_cur, 5, t, s);                        // issued
+                }
+                // K/V tiles this Q tile never touches (tile 0 under the causal mask) still need its release.  Wait
+                // for each to land first: an arrival for a ring entry that is not loaded yet would be counted in
+                // the slot's previous phase and free it under the other tile.
+                for (int j = (nt + 1) >> 1; j < it.n_kv; ++j) {
+                    wait_kv(2 * j);
+                    wait_kv(2 * j + 1);
+                    if (elect_one()) {
+                        umma_commit(&kv_empty[slot_of(2 * j)]);
+                        umma_commit(&kv_empty[slot_of(2 * j + 1)]);
                     }
                     __syncwarp();
                 }
-                for (int j = 0; j < n1; ++j) {
-                    // K/V of this step: normally landed long ago (the ring runs ~1.5 steps ahead)
-                    wait_kv(2 * j + 1);
-                    if (j + 1 < n1) wait_kv(2 * j + 2);
-#pragma unroll 1
-                    for (int t = 0; t < 2; ++t) {
-                        const int nt = t ? n1 : n0;
-                        if (j >= nt) continue;
-                        mbar_wait(&pv_ok[t], (p_par >> t) & 1);
-                        p_par ^= 1u << t;
-                        const bool more = j + 1 < nt;
-                        tc_fence_after();
-                        trace_event(p, lane, 2, trace_cur, 4, t, j);                        // inputs of PV_t(j) ready
-                        if (elect_one()) {
-                            issue_PV(t, slot_of(2 * j + 1), j > 0 ? 1u : 0u);              // O_t += P_t(j) V_j
-                            if (!more) umma_commit(&o_final[t]);
-                            if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 1)]);
-                            if (more) {
-                                issue_S(t, slot_of(2 * j + 2));                          // S_t(j+1) = Q_t K_{j+1}^T
-                                umma_commit(&s_full[t]);
-                                if (j + 2 == nt) umma_commit(&q_empty[t]);
-                                if (t == 1) umma_commit(&kv_empty[slot_of(2 * j + 2)]);
-                            }
-                        }
-                        __syncwarp();
-                        trace_event(p, lane, 2, trace_cur, 5, t, j);                        // issued
-                    }
-                }
-                kv_cnt += 2 * n1;
+                kv_cnt += 2 * it.n_kv;
             }
-        } else if (warp == 13 && lane == 0) {
+        } else if (warp == 14 && lane == 0) {
             // =========================== TMA producer ===========================
             prefetch_tensormap(&map_q);
             prefetch_tensormap(&map_k);
             prefetch_tensormap(&map_v);
             prefetch_tensormap(&map_o);
             uint32_t kv_cnt = 0, item_par = 0;
-            for (int w = blockIdx.x; w < p.total_items; w += gridDim.x, item_par ^= 1) {
+            for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
-                const int n_max = it.n[1];
                 auto load_q = [&](int t) {
-                    mbar_wait(&q_empty[t], item_par ^ 1);
+                    mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
                     mbar_arrive_expect_tx(&q_full[t], kTileBytes);
 #pragma unroll
                     for (int hf = 0; hf < kHalves; ++hf)
@@ -491,7 +498,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 };
                 auto load_kv = [&](const CUtensorMap* map, int j) {
                     const uint32_t slot = kv_cnt % kStages;
-                    mbar_wait(&kv_empty[slot], ((kv_cnt / kStages) & 1) ^ 1);
+                    mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
 #pragma unroll
                     for (int hf = 0; hf < kHalves; ++hf)
@@ -503,7 +510,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 load_kv(&map_k, 0);
                 load_q(1);
                 load_kv(&map_v, 0);
-                for (int j = 1; j < n_max; ++j) {
+                for (int j = 1; j < it.n_kv; ++j) {
                     load_kv(&map_k, j);
                     load_kv(&map_v, j);
                 }

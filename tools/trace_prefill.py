@@ -37,7 +37,7 @@ t0 = recs[0][0]
 names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "mma: V landed", 7: "mma: O corrected", 8: "mma: P seen"}
 print("first item (64 KV tiles for tile 1): events of steps 20..23")
 for clk, ev, t, j in recs:
-    if 21 <= j <= 22 and clk - t0 < 800000:
+    if 40 <= j <= 44 and clk - t0 < 800000:
         print(f"  {clk - t0:8d}  tile{t} j={j:3d} {names[ev]}")
 # statistics over the first item: per-tile durations
 import collections
@@ -53,7 +53,7 @@ for clk, e, t, j in first_item:
 def avg(xs):
     return sum(xs) / max(1, len(xs))
 for t in (0, 1):
-    js = sorted(j for (tt, j) in ev if tt == t and 5 <= j <= 55)
+    js = sorted(j for (tt, j) in ev if tt == t and 10 <= j <= 110)
     soft = [ev[(t, j)][3] - ev[(t, j)][1] for j in js if 3 in ev[(t, j)] and 1 in ev[(t, j)]]
     mx = [ev[(t, j)][2] - ev[(t, j)][1] for j in js if 2 in ev[(t, j)] and 1 in ev[(t, j)]]
     p2go = [ev[(t, j)][4] - ev[(t, j)][3] for j in js if 4 in ev[(t, j)] and 3 in ev[(t, j)]]
