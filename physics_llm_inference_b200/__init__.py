@@ -16,6 +16,7 @@ from .decode import (decode_kernel_kind, decode_num_splits, decode_with_cache, d
 from .flash_attention import (FlashAttentionConfig, attention_flops, flash_attention, flash_attention_forward,
                               flash_attention_memory_bytes, prefill_algorithmic_flops, prefill_kernel_kind)
 from .kv_cache import KVCache, LayerKVCache, create_caches, kv_append
+from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention
 from .paged_memory import BlockTable, PagedKVCache
 from .sharding import HeadShard, gather_heads, init_distributed, make_shard, shard_kv_heads
 
@@ -25,6 +26,7 @@ __all__ = [
     "flash_decode", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
     "decode_kernel_kind", "paged_gather",
     "KVCache", "LayerKVCache", "create_caches", "kv_append", "BlockTable", "PagedKVCache",
+    "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner",
     "HeadShard", "make_shard", "shard_kv_heads", "gather_heads", "init_distributed",
     "PliError", "LIB_PATH", "launch_count", "reset_launch_count",
 ]

@@ -1,0 +1,94 @@
+"""Callers of the hot path: the reference's GQA blocks with the attention core on the
+kernels, against the reference's own outputs (golden, identity projection weights), and the CUDA-graph
+decode step against eager execution."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import physics_llm_inference_b200 as pli
+from oracle import attention_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _identity_weights(mod, Hq, Hkv, D):
+    hid = Hq * D
+    with torch.no_grad():
+        mod.q_proj.weight.copy_(torch.eye(hid))
+        mod.o_proj.weight.copy_(torch.eye(hid))
+        mod.k_proj.weight.zero_()
+        mod.v_proj.weight.zero_()
+        mod.k_proj.weight[:, :Hkv * D] = torch.eye(Hkv * D)
+        mod.v_proj.weight[:, Hkv * D:2 * Hkv * D] = torch.eye(Hkv * D)
+
+
+def _bhnd(y, Hq, D):
+    B, N, _ = y.shape
+    return y.view(B, N, Hq, D).transpose(1, 2)
+
+
+def test_gqa_module_matches_reference_module(golden_dir):
+    """ch01.gqa.GroupedQueryAttention, unmodified, produced tests/golden/ch01_gqa.npz with these weights."""
+    g = np.load(os.path.join(golden_dir, "ch01_gqa.npz"))
+    B, Hq, Hkv, N, D = [int(x) for x in g["meta"]]
+    mod = pli.GroupedQueryAttention(Hq * D, Hq, Hkv).cuda()
+    _identity_weights(mod, Hq, Hkv, D)
+    x = torch.from_numpy(g["x"]).cuda()
+    with torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        y_c = _bhnd(mod(x, causal=True), Hq, D).cpu()
+        y_f = _bhnd(mod(x, causal=False), Hq, D).cpu()
+    assert (y_c - torch.from_numpy(g["causal"])).abs().max().item() <= 1e-3
+    assert (y_f - torch.from_numpy(g["full"])).abs().max().item() <= 1e-3
+    assert mod.kv_cache_size_per_token(torch.float16) == 2 * Hkv * D * 2     # ch01/test_ch01.py:79-88
+
+
+def test_cached_gqa_module_matches_reference_module(golden_dir):
+    """ch02.cached_generation.CachedGQA: prefill 37, chunk 11, decode 1, decode 1 (tests/golden/ch02_cached.npz)."""
+    g = np.load(os.path.join(golden_dir, "ch02_cached.npz"))
+    B, Hq, Hkv, D, Lmax = [int(x) for x in g["meta"]]
+    mod = pli.CachedGQA(Hq * D, Hq, Hkv).cuda()
+    _identity_weights(mod, Hq, Hkv, D)
+    cache = pli.create_caches(1, B, Lmax, Hkv, D, "cuda", torch.float32)[0]
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pos = 0
+    with torch.no_grad():
+        for step in range(4):
+            x = torch.from_numpy(g[f"x{step}"]).cuda()
+            y = _bhnd(mod(x, cache, pos), Hq, D).cpu()
+            pos += x.shape[1]
+            assert cache.seq_len == pos                                      # ch02/test_ch02.py:165-204
+            assert (y - torch.from_numpy(g[f"y{step}"])).abs().max().item() <= 1e-3, step
+    assert torch.equal(cache.k.cpu(), torch.from_numpy(g["k_cache"]))
+
+
+@pytest.mark.parametrize("paged", [False, True])
+def test_decode_step_under_cuda_graph(paged):
+    B, Hq, Hkv, D, bs, L0, steps = 4, 8, 2, 128, 16, 70, 5
+    g = torch.Generator().manual_seed(41)
+    dt = torch.bfloat16
+    if paged:
+        pages_per = 8
+        P = B * pages_per
+        kc = torch.zeros(P, 1, bs, Hkv, D, dtype=dt, device="cuda")
+        vc = torch.zeros_like(kc)
+        table = torch.randperm(P, generator=g).to(torch.int32).view(B, pages_per).cuda()
+    else:
+        kc = torch.zeros(B, 128, Hkv, D, dtype=dt, device="cuda")
+        vc = torch.zeros_like(kc)
+        table = None
+    k_hist = torch.randn(B, L0 + steps, Hkv, D, generator=g).to(dt).cuda()
+    v_hist = torch.randn(B, L0 + steps, Hkv, D, generator=g).to(dt).cuda()
+    pli.kv_append(kc, vc, k_hist[:, :L0], v_hist[:, :L0], 0, block_tables=table)
+    runner = pli.DecodeGraphRunner(kc, vc, Hq, block_tables=table)
+    lens = torch.full((B,), L0, dtype=torch.int32, device="cuda")
+    assert runner.capture(lens)
+    for i in range(steps):
+        q = torch.randn(B, Hq, 1, D, generator=g).to(dt).cuda()
+        out = runner.run(q, k_hist[:, L0 + i:L0 + i + 1], v_hist[:, L0 + i:L0 + i + 1])
+        L = L0 + i + 1
+        ref, _ = orc.cached_attention_oracle(q, k_hist, v_hist, L)
+        assert (out.float().cpu() - ref[:, :, 0]).abs().max().item() <= 2e-2, i
+    assert int(runner.seq_lens[0]) == L0 + steps
