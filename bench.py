@@ -41,6 +41,25 @@ CPU_SAMPLE = dict(B=1, Hq=32, Hkv=8, N=8192, D=128)
 CPU_DECODE_SAMPLE = dict(B=16, Hq=32, Hkv=8, L=4096, D=128, bs=16)
 
 
+_JSON_FD = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout; NCCL and friends print banners there.  Route fd 1 to stderr for
+    the whole run and keep the real stdout for the final line."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -196,7 +215,74 @@ def run_reference(args, rank: int):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "host": {"cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
+    """BASELINE configs 4 and 5: fixed total work, KV heads sharded over the ranks (8/W KV heads + their 32/W q
+    heads per GPU), no data-path collective; the optional NCCL all-gather of O is timed separately.
+    Reported per config: whole-job rate = total algorithmic work / max-over-ranks kernel time."""
+    import torch
+    Hq, Hkv, D = 32, 8, 128
+    if Hkv % world != 0:
+        return {"skipped": f"{Hkv} KV heads do not divide over {world} ranks"}
+    shard = pli.make_shard(rank, world, Hq, Hkv, 1)
+    hq_l, hkv_l = shard.q_end - shard.q_start, shard.kv_end - shard.kv_start
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = {}
+
+    def timed(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1) / reps)
+
+    # C4: long-context causal prefill, N = 65536, B = 1
+    N = 65536
+    g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 4 + rank)
+    q = torch.randn(1, hq_l, N, D, device=dev, generator=g).bfloat16()
+    k = torch.randn(1, hkv_l, N, D, device=dev, generator=g).bfloat16()
+    v = torch.randn(1, hkv_l, N, D, device=dev, generator=g).bfloat16()
+    ms = timed(lambda: pli.flash_attention_forward(q, k, v, causal=True), 2, 5)
+    flops = pli.prefill_algorithmic_flops(1, Hq, N, N, D, True)
+    entry = {"workload": "C4: causal GQA prefill N65536 B1 32q/8kv D128 bf16, KV heads sharded", "ms": ms,
+             "tflops_total": flops / (ms * 1e-3) / 1e12, "tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12}
+    if world > 1:
+        o = pli.flash_attention_forward(q, k, v, causal=True)
+        entry["gather_ms"] = timed(lambda: pli.gather_heads(o, shard), 1, 3)
+        entry["gather_bytes_total"] = Hq * N * D * 2
+    out["c4_prefill_65536"] = entry
+    del q, k, v
+
+    # C5: decode B256, paged, ctx sweep
+    B, bs = 256, 16
+    rows = []
+    for L in (1024, 8192, 32768):
+        pages = B * L // bs
+        kp = torch.empty(pages, 1, bs, hkv_l, D, device=dev, dtype=torch.bfloat16).normal_(generator=g)
+        vp = torch.empty(pages, 1, bs, hkv_l, D, device=dev, dtype=torch.bfloat16).normal_(generator=g)
+        table = torch.randperm(pages, generator=torch.Generator().manual_seed(7)).to(torch.int32).view(B, L // bs).to(dev)
+        lens = torch.full((B,), L, dtype=torch.int32, device=dev)
+        qd = torch.randn(B, hq_l, 1, D, device=dev, generator=g).bfloat16()
+        splits = pli.decode_num_splits(B, hkv_l, L)
+        ws = pli.decode_workspace(B, hq_l, D, splits, dev)
+        od = torch.empty(B, hq_l, D, device=dev, dtype=torch.bfloat16)
+        fn = lambda: pli.flash_decode(qd, kp, vp, lens, block_tables=table, max_seq_len=L, workspace=ws, out=od)  # noqa: E731
+        ms = timed(fn, 3, 20 if L < 32768 else 8)
+        nbytes = decode_bytes(B, Hq, Hkv, L, D, bs)
+        row = {"ctx": L, "us": ms * 1e3, "gbs_total": nbytes / (ms * 1e-3) / 1e9, "gbs_per_gpu": nbytes / world / (ms * 1e-3) / 1e9,
+               "kv_bytes_per_gpu": 2 * pages * bs * hkv_l * D * 2, "l2_note": "single pool; >L2 except ctx 1024 at 8 GPUs"}
+        if world > 1:
+            row["gather_us"] = timed(lambda: pli.gather_heads(od, shard), 2, 10) * 1e3
+        rows.append(row)
+        del kp, vp
+    out["c5_decode_b256"] = {"workload": "C5: paged decode B256, 32q/8kv D128, 16-token pages, KV heads sharded", "sweep": rows}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -211,8 +297,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    protect_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -358,6 +446,11 @@ def main():
                                "note": "split-KV kernel + combine kernel timed together; algorithmic bytes = K,V once + q,o + table"}}
         del pools
 
+    # ---- strong-scaling configs of BASELINE.json (C4 long-context prefill, C5 decode sweep), KV heads sharded ----
+    strong = None
+    if not args.no_strong:
+        strong = run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -384,6 +477,8 @@ def main():
     }
     if sustained is not None:
         line["sustained"] = sustained
+    if strong is not None:
+        line["strong_scaling_configs"] = strong
     if decode is not None:
         line["decode"] = decode
     if not args.no_cpu_baseline and world == 1:
@@ -398,7 +493,7 @@ def main():
             line["decode"]["cpu_baseline"] = {"value": dval, "unit": "GB/s", "cores": threads, "kind": "port",
                                               "sample": f"oracle port (ch07 page gather + ch02 cached attention, fp32) on "
                                                         f"{s['B']} of the 64 sequences, {ddt:.2f} s"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
