@@ -53,7 +53,7 @@ struct SmemLayout {
     static constexpr int kSumOff = kScaleOff + 4 * 128 * 4;        // float [2][128]
     static constexpr int kMaxOff = kSumOff + 2 * 128 * 4;          // float [2][128]
     static constexpr int kBarOff = kMaxOff + 2 * 128 * 4;
-    static constexpr int kNumBars = 4 + 2 * kKVStages + 16;
+    static constexpr int kNumBars = 4 + 2 * kKVStages + 22;
     static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kTmemPtrOff + 16;
 };
@@ -160,8 +160,14 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     // correction-warp arrivals (O_t rescaled for s >= 1; drained by the previous item / free at start for s == 0).
     uint64_t* pv_ok = s_full + 4;             // [4]
     uint64_t* sc_full = pv_ok + 4;            // [4]  softmax (4 warps) -> correction: scale factor of step s posted
-    uint64_t* o_final = sc_full + 4;          // [2]  MMA (commit) -> correction: last PV of the item done
+    // pv_done: PV_t(s) has completed.  S runs two half-steps ahead, so the softmax of step s can post its scale
+    // factor while PV_t(s-1) is still accumulating into O_t; the correction warps must see PV_t(s-1) complete
+    // before they rescale O_t (they consume the phases lazily: a blocking wait only when a rescale is needed).
+    uint64_t* pv_done = sc_full + 4;          // [4]  MMA (commit) -> correction
+    uint64_t* o_final = pv_done + 4;          // [2]  MMA (commit) -> correction: last PV of the item done
     uint64_t* stats_full = o_final + 2;       // [2]  softmax (4 warps) -> correction: row sum / max posted
+    uint64_t* stats_free = stats_full + 2;    // [2]  correction (4 warps) -> softmax: the stats slots were read (a short
+                                              //      next item could otherwise finish before this one's epilogue ran)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,11 +178,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             mbar_init(&q_empty[i], 1);
             mbar_init(&o_final[i], 1);
             mbar_init(&stats_full[i], 4);
+            mbar_init(&stats_free[i], 4);
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&pv_ok[i], 8);
             mbar_init(&sc_full[i], 4);
+            mbar_init(&pv_done[i], 1);
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&kv_full[i], 1);
@@ -207,6 +215,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         uint32_t sf_par = 0;                              // bit h: phase parity of s_full[t*2+h]
         int trace_cur = 0;
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd) {
+            const uint32_t item_par = rnd & 1;
             const WorkItem it = decode_item(w, p);
             const int q_tile0 = it.q0 + t * kBM;
             const int q_row = q_tile0 + row;
@@ -286,6 +295,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 if (lane == 0) mbar_arrive(&pv_ok[t * 2 + h]);
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 3, t, s);       // P posted
             }
+            mbar_wait(&stats_free[t], item_par ^ 1);      // previous item's epilogue has read the slots
             sSum[t * 128 + row] = d;
             sMax[t * 128 + row] = m_ref * c;              // log2 units
             __syncwarp();
@@ -297,13 +307,22 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        uint32_t sc_par = 0, item_cnt = 0;                // sc_par bit t*2+h: phase parity of sc_full[t*2+h]
+        uint32_t sc_par = 0, pd_par = 0, item_cnt = 0;    // bit t*2+h: phase parity of sc_full / pv_done [t*2+h]
         if (lane == 0) {                                  // first item: O_0 / O_1 are free
             mbar_arrive(&pv_ok[0]);
             mbar_arrive(&pv_ok[2]);
         }
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, ++item_cnt) {
             const WorkItem it = decode_item(w, p);
+            int pv_seen[2] = {0, 0};                      // PV_t(0 .. pv_seen[t]-1) of this item are known complete
+            auto consume_pv_done = [&](int t, int upto) {
+                while (pv_seen[t] < upto) {
+                    const int bi = t * 2 + (pv_seen[t] & 1);
+                    mbar_wait_relaxed(&pv_done[bi], (pd_par >> bi) & 1);
+                    pd_par ^= 1u << bi;
+                    ++pv_seen[t];
+                }
+            };
             for (int s = 1; s < it.n[1]; ++s) {
                 const int h = s & 1;
 #pragma unroll
@@ -313,7 +332,11 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     mbar_wait_relaxed(&sc_full[bi], (sc_par >> bi) & 1);
                     sc_par ^= 1u << bi;
                     const float alpha = sScale[bi * 128 + row];
-                    if (__any_sync(0xffffffffu, alpha != 1.f)) {
+                    const bool rescale = __any_sync(0xffffffffu, alpha != 1.f);
+                    // PV_t(s-2) finished long ago (keeps the barrier parity in step); PV_t(s-1) only matters
+                    // when O_t is about to be rescaled
+                    consume_pv_done(t, rescale ? s : s - 1);
+                    if (rescale) {
                         tc_fence_after();
 #pragma unroll
                         for (int ch = 0; ch < kD / 32; ++ch) {
@@ -336,9 +359,12 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (int t = 0; t < 2; ++t) {
                 mbar_wait_relaxed(&stats_full[t], item_cnt & 1);
                 mbar_wait_relaxed(&o_final[t], item_cnt & 1);
+                consume_pv_done(t, it.n[t]);
                 tc_fence_after();
                 const float dsum = sSum[t * 128 + row];
                 const float mlog2 = sMax[t * 128 + row];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&stats_free[t]);
                 const float inv = 1.f / dsum;
                 const int q_tile0 = it.q0 + t * kBM;
 #pragma unroll
@@ -455,6 +481,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     trace_event(p, lane, 2 + t, trace_cur, 4, t, s);                        // inputs of PV_t(s) ready
                     if (elect_one()) {
                         issue_PV(s, slot_of(2 * (s >> 1) + 1));
+                        umma_commit(&pv_done[t * 2 + h]);
                         if (s == nt - 1) umma_commit(&o_final[t]);
                         if (h || s == nt - 1) umma_commit(&kv_empty[slot_of(2 * (s >> 1) + 1)]);   // V tile done (this Q tile)
                         if (more) {

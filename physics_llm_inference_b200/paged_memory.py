@@ -44,6 +44,8 @@ class PagedKVCache:
 
         self.free_blocks: set[int] = set(range(num_blocks))
         self.block_tables: dict[int, BlockTable] = {}
+        # pages referenced by more than one block table (prefix sharing); absent = 1 owner
+        self.shared_refs: dict[int, int] = {}
 
         # ch07/paged_memory.py:38-51: tensors only when CUDA is there and asked for
         if torch.cuda.is_available() and str(device).startswith("cuda"):
@@ -85,8 +87,44 @@ class PagedKVCache:
             return 0
         table = self.block_tables.pop(request_id)
         for block_idx in table.block_indices:
-            self.free_blocks.add(block_idx)
+            refs = self.shared_refs.get(block_idx, 1) - 1
+            if refs >= 1:                     # still referenced by another request's table
+                if refs == 1:
+                    del self.shared_refs[block_idx]
+                else:
+                    self.shared_refs[block_idx] = refs
+            else:
+                self.free_blocks.add(block_idx)
         return len(table.block_indices)
+
+    def fork_request(self, parent_id: int, child_id: int, num_tokens: int | None = None) -> BlockTable:
+        """Start `child_id` with the first `num_tokens` cached tokens of `parent_id` (a matched prefix, as
+        `RadixCache.match_prefix` of ch07/radix_cache.py:72-103 reports it) WITHOUT recomputing or copying
+        them: full pages are aliased (both block tables point at the same physical page, ref-counted),
+        a partially filled last page is copied so the child can append to it.  The read path needs no
+        change: the kernels only ever see a block table."""
+        if parent_id not in self.block_tables:
+            raise KeyError(f"Request {parent_id} not found")
+        parent = self.block_tables[parent_id]
+        n = parent.num_tokens if num_tokens is None else num_tokens
+        if not 0 <= n <= parent.num_tokens:
+            raise ValueError(f"cannot share {n} tokens of a request with {parent.num_tokens}")
+        full, rem = divmod(n, self.block_size)
+        if rem and not self.free_blocks:
+            raise RuntimeError("Not enough free blocks: need 1, have 0")
+        pages = list(parent.block_indices[:full])
+        for pg in pages:
+            self.shared_refs[pg] = self.shared_refs.get(pg, 1) + 1
+        if rem:
+            new_page = self.free_blocks.pop()
+            if self.k_cache is not None:
+                src = parent.block_indices[full]
+                self.k_cache[new_page].copy_(self.k_cache[src])
+                self.v_cache[new_page].copy_(self.v_cache[src])
+            pages.append(new_page)
+        table = BlockTable(request_id=child_id, block_indices=pages, num_tokens=n)
+        self.block_tables[child_id] = table
+        return table
 
     def get_num_free_blocks(self) -> int:
         return len(self.free_blocks)

@@ -194,3 +194,31 @@ def test_c3_full_size_properties():
     table2 = inv.cuda()[table.long()].to(torch.int32)
     o2 = pli.flash_decode(q, kp2, vp2, lens, block_tables=table2, max_seq_len=L)
     assert torch.equal(o2, o)
+
+
+def test_shared_prefix_pages_alias():
+    """F3: two requests whose block tables alias the same physical prefix pages decode like unshared ones."""
+    Hq, Hkv, D, bs = 8, 2, 128, 16
+    cache = pli.PagedKVCache(num_blocks=32, block_size=bs, num_layers=1, num_heads=Hkv, head_dim=D,
+                             dtype=torch.bfloat16, device="cuda")
+    g = torch.Generator().manual_seed(51)
+    L0, extra = 70, 9                                       # 4 full pages + 6 tokens
+    k0 = torch.randn(1, L0, Hkv, D, generator=g).bfloat16().cuda()
+    v0 = torch.randn(1, L0, Hkv, D, generator=g).bfloat16().cuda()
+    cache.append([1], k0, v0)
+    cache.fork_request(1, 2, 67)                            # child shares 67 tokens: 4 aliased pages + copied tail
+    assert cache.block_tables[2].block_indices[:4] == cache.block_tables[1].block_indices[:4]
+    k2 = torch.randn(1, extra, Hkv, D, generator=g).bfloat16().cuda()
+    v2 = torch.randn(1, extra, Hkv, D, generator=g).bfloat16().cuda()
+    cache.append([2], k2, v2)
+    q = torch.randn(2, Hq, 1, D, generator=g).bfloat16().cuda()
+    o = pli.decode_with_paged(q, cache, [1, 2])
+    ref1, _ = orc.cached_attention_oracle(q[:1], k0, v0, L0)
+    kk = torch.cat([k0[:, :67], k2], 1)
+    vv = torch.cat([v0[:, :67], v2], 1)
+    ref2, _ = orc.cached_attention_oracle(q[1:], kk, vv, 67 + extra)
+    assert (o[:1].float().cpu() - ref1).abs().max().item() <= 2e-2
+    assert (o[1:].float().cpu() - ref2).abs().max().item() <= 2e-2
+    # the parent's pages were not disturbed by the child's appends
+    got = pli.paged_gather(cache.k_cache, *cache.block_table_tensor([1]), L0)
+    assert torch.equal(got[0], k0[0])

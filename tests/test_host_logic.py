@@ -158,3 +158,27 @@ def test_missing_library_is_an_error(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.PliError, match="no CPU fallback"):
         _lib.load()
+
+
+def test_prefix_sharing_refcounts():
+    """F3: page-granular prefix sharing on top of the reference allocator (host bookkeeping)."""
+    c = pli.PagedKVCache(num_blocks=10, block_size=16, num_layers=1, num_heads=2, head_dim=8, device="cpu")
+    c.allocate_blocks(1, 40)                                  # 3 pages, last one holds 8 tokens
+    t2 = c.fork_request(1, 2, 35)                             # 2 full pages shared + 1 private copy page
+    assert t2.num_tokens == 35 and t2.num_blocks() == 3
+    assert t2.block_indices[:2] == c.block_tables[1].block_indices[:2]
+    assert t2.block_indices[2] != c.block_tables[1].block_indices[2]
+    assert c.get_num_free_blocks() == 10 - 3 - 1
+    c.extend_blocks(2, 20)                                    # child grows on its own pages
+    assert c.block_tables[2].num_blocks() == 4
+    assert c.free_blocks_for_request(1) == 3                  # parent leaves: shared pages stay alive
+    assert c.get_num_free_blocks() == 10 - 4
+    t3 = c.fork_request(2, 3)                                 # share everything (55 tokens: 3 full + copy)
+    assert t3.block_indices[:3] == c.block_tables[2].block_indices[:3]
+    c.free_blocks_for_request(2)
+    c.free_blocks_for_request(3)
+    assert c.get_num_free_blocks() == 10 and not c.shared_refs
+    with pytest.raises(KeyError):
+        c.fork_request(9, 4)
+    with pytest.raises(ValueError):
+        c.allocate_blocks(5, 10) and c.fork_request(5, 6, 11)
