@@ -160,10 +160,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     // correction-warp arrivals (O_t rescaled for s >= 1; drained by the previous item / free at start for s == 0).
     uint64_t* pv_ok = s_full + 4;             // [4]
     uint64_t* sc_full = pv_ok + 4;            // [4]  softmax (4 warps) -> correction: scale factor of step s posted
-    // pv_done: PV_t(s) has completed.  S runs two half-steps ahead, so the softmax of step s can post its scale
-    // factor while PV_t(s-1) is still accumulating into O_t; the correction warps must see PV_t(s-1) complete
-    // before they rescale O_t (they consume the phases lazily: a blocking wait only when a rescale is needed).
-    uint64_t* pv_done = sc_full + 4;          // [4]  MMA (commit) -> correction
+    // Rescaling O_t at half-step s needs PV_t(s-1) complete, and with S running two half-steps ahead the
+    // softmax of step s does not imply that.  But S_t(s+1) is issued right behind PV_t(s-1), so the commit of
+    // s_full for step s+1 covers it: the correction warps wait on that phase (without consuming it) in the rare
+    // steps that rescale.  The last step has no S behind its predecessor PV: pv_tail[t] is committed once per
+    // item right after PV_t(n-2).
+    uint64_t* pv_tail = sc_full + 4;          // [2]  MMA (commit) -> correction (+2 spare slots)
+    uint64_t* pv_done = pv_tail;              // (alias kept for the barrier-array layout below)
     uint64_t* o_final = pv_done + 4;          // [2]  MMA (commit) -> correction: last PV of the item done
     uint64_t* stats_full = o_final + 2;       // [2]  softmax (4 warps) -> correction: row sum / max posted
     uint64_t* stats_free = stats_full + 2;    // [2]  correction (4 warps) -> softmax: the stats slots were read (a short
@@ -184,7 +187,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             mbar_init(&s_full[i], 1);
             mbar_init(&pv_ok[i], 8);
             mbar_init(&sc_full[i], 4);
-            mbar_init(&pv_done[i], 1);
+            mbar_init(&pv_tail[i], 1);        // [0..1] used
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&kv_full[i], 1);
@@ -307,22 +310,14 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int wq = warp & 3;
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-        uint32_t sc_par = 0, pd_par = 0, item_cnt = 0;    // bit t*2+h: phase parity of sc_full / pv_done [t*2+h]
+        uint32_t sc_par = 0, item_cnt = 0;                // sc_par bit t*2+h: phase parity of sc_full[t*2+h]
+        uint32_t sf_base = 0;                             // bit t*2+h: parity of s_full[t*2+h]'s first phase in this item
         if (lane == 0) {                                  // first item: O_0 / O_1 are free
             mbar_arrive(&pv_ok[0]);
             mbar_arrive(&pv_ok[2]);
         }
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, ++item_cnt) {
             const WorkItem it = decode_item(w, p);
-            int pv_seen[2] = {0, 0};                      // PV_t(0 .. pv_seen[t]-1) of this item are known complete
-            auto consume_pv_done = [&](int t, int upto) {
-                while (pv_seen[t] < upto) {
-                    const int bi = t * 2 + (pv_seen[t] & 1);
-                    mbar_wait_relaxed(&pv_done[bi], (pd_par >> bi) & 1);
-                    pd_par ^= 1u << bi;
-                    ++pv_seen[t];
-                }
-            };
             for (int s = 1; s < it.n[1]; ++s) {
                 const int h = s & 1;
 #pragma unroll
@@ -333,10 +328,14 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     sc_par ^= 1u << bi;
                     const float alpha = sScale[bi * 128 + row];
                     const bool rescale = __any_sync(0xffffffffu, alpha != 1.f);
-                    // PV_t(s-2) finished long ago (keeps the barrier parity in step); PV_t(s-1) only matters
-                    // when O_t is about to be rescaled
-                    consume_pv_done(t, rescale ? s : s - 1);
                     if (rescale) {
+                        // PV_t(s-1) must have completed: covered by the commit behind S_t(s+1), or by pv_tail
+                        if (s + 1 < it.n[t]) {
+                            const int bj = t * 2 + (h ^ 1);
+                            mbar_wait(&s_full[bj], ((sf_base >> bj) ^ ((s + 1) >> 1)) & 1);
+                        } else {
+                            mbar_wait(&pv_tail[t], item_cnt & 1);
+                        }
                         tc_fence_after();
 #pragma unroll
                         for (int ch = 0; ch < kD / 32; ++ch) {
@@ -359,7 +358,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (int t = 0; t < 2; ++t) {
                 mbar_wait_relaxed(&stats_full[t], item_cnt & 1);
                 mbar_wait_relaxed(&o_final[t], item_cnt & 1);
-                consume_pv_done(t, it.n[t]);
+                mbar_wait_relaxed(&pv_tail[t], item_cnt & 1);         // one phase per item: keeps its parity in step
                 tc_fence_after();
                 const float dsum = sSum[t * 128 + row];
                 const float mlog2 = sMax[t * 128 + row];
@@ -405,6 +404,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 if (p.lse != nullptr && q_tile0 + row < p.Nq)
                     p.lse[((int64_t)it.b * p.Hq + it.h) * p.Nq + q_tile0 + row] = (mlog2 + log2f(dsum)) * kLn2;
+                // s_full[t*2+h] completed ceil((n_t - h) / 2) phases in this item
+                sf_base ^= (uint32_t)(((it.n[t] + 1) >> 1) & 1) << (t * 2);
+                sf_base ^= (uint32_t)((it.n[t] >> 1) & 1) << (t * 2 + 1);
             }
         }
         if (warp == 8 && lane == 0) tma_store_wait_all<0>();
@@ -481,7 +483,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     trace_event(p, lane, 2 + t, trace_cur, 4, t, s);                        // inputs of PV_t(s) ready
                     if (elect_one()) {
                         issue_PV(s, slot_of(2 * (s >> 1) + 1));
-                        umma_commit(&pv_done[t * 2 + h]);
+                        if (s + 2 == nt || nt == 1) umma_commit(&pv_tail[t]);           // no S follows this PV
                         if (s == nt - 1) umma_commit(&o_final[t]);
                         if (h || s == nt - 1) umma_commit(&kv_empty[slot_of(2 * (s >> 1) + 1)]);   // V tile done (this Q tile)
                         if (more) {
