@@ -491,7 +491,7 @@ def main():
                                "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
                                "frac_of_8tbs": gbs / 8000.0, "traffic": load_traffic("decode_tma_kernel<128,bf16> C3"),
                                "algorithmic_bytes": nbytes,
-                               "note": "split-KV kernel + combine kernel timed together; algorithmic bytes = K,V once + q,o + table"}}
+                               "note": "one split-KV launch per step (a single split writes the output directly; the combine pass runs only when num_splits > 1); algorithmic bytes = K,V once + q,o + table"}}
         del pools
 
     # ---- strong-scaling configs of BASELINE.json (C4 long-context prefill, C5 decode sweep), KV heads sharded ----
