@@ -18,6 +18,7 @@
 // smem: Q 2 x [128 x D], K/V ring of 4 (D=128) / 8 (D=64) [128 x D] tiles, one [128 x 64] O staging
 // sub-tile; every tile is stored as D/64 sub-tiles of [128 rows][64 el] with the 128-byte swizzle
 // that TMA and UMMA share.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -140,7 +141,11 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
     return it;
 }
 
-template <int kD, bool kBf16>
+// kCluster = 2: CTA pairs (thread-block clusters of two, same TPC) work on two q heads of the SAME KV group at
+// the same Q-tile pair, so they need the same K/V tiles: each CTA TMA-loads half of every tile and MULTICASTS it
+// into both CTAs' shared memory (L2 -> SM traffic of K/V halves), and a ring slot is refilled once the MMA warps
+// of both CTAs have released it (tcgen05.commit multicast onto both CTAs' kv_empty barriers).
+template <int kD, bool kBf16, int kCluster>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
@@ -203,7 +208,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 2);
+            mbar_init(&kv_empty[i], 2 * kCluster);    // both MMA warps of every CTA in the cluster
         }
         fence_barrier_init();
     }
@@ -213,6 +218,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     // TMEM: S_t buffer h at column t*128 + h*64 (P aliases its first 32 columns); O_t at 256 + t*128.
@@ -440,6 +446,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const uint32_t v_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboV;
             const uint32_t tmem_s = tmem_base + t * 128, tmem_o = tmem_base + 256 + t * 128;
             uint32_t kv_cnt = 0, item_par = 0, pv_par = 0;        // pv_par bit h: phase parity of pv_ok[t*2+h]
+            auto release_kv = [&](uint64_t* bar) {                // this Q tile is done with a ring slot
+                if constexpr (kCluster > 1) umma_commit_multicast(bar, (uint16_t)((1u << kCluster) - 1));
+                else umma_commit(bar);
+            };
             int trace_cur = 0;
             auto issue_S = [&](int s, uint32_t kslot) {
                 // S_t(s) = Q_t K[rows 64 (s&1) .. +64 of the tile]^T : K-major, 32 bytes of head_dim per MMA
@@ -468,7 +478,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // K tile j is ring entry 2j, V tile j is ring entry 2j+1.  after_S(s): bookkeeping once S_t(s) is issued
                 auto after_S = [&](int s) {
                     umma_commit(&s_full[t * 2 + (s & 1)]);
-                    if ((s & 1) || s == nt - 1) umma_commit(&kv_empty[slot_of(2 * (s >> 1))]);   // K tile done (this Q tile)
+                    if ((s & 1) || s == nt - 1) release_kv(&kv_empty[slot_of(2 * (s >> 1))]);   // K tile done (this Q tile)
                     if (s == nt - 1) umma_commit(&q_empty[t]);
                 };
                 // ---- prologue: S_t(0), S_t(1) from K tile 0 ----
@@ -497,7 +507,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         issue_PV(s, slot_of(2 * (s >> 1) + 1));
                         if (s + 2 == nt || nt == 1) umma_commit(&pv_tail[t]);           // no S follows this PV
                         if (s == nt - 1) umma_commit(&o_final[t]);
-                        if (h || s == nt - 1) umma_commit(&kv_empty[slot_of(2 * (s >> 1) + 1)]);   // V tile done (this Q tile)
+                        if (h || s == nt - 1) release_kv(&kv_empty[slot_of(2 * (s >> 1) + 1)]);   // V tile done (this Q tile)
                         if (more) {
                             issue_S(s + 2, slot_of(2 * ((s + 2) >> 1)));
                             after_S(s + 2);
@@ -513,8 +523,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     wait_kv(2 * j);
                     wait_kv(2 * j + 1);
                     if (elect_one()) {
-                        umma_commit(&kv_empty[slot_of(2 * j)]);
-                        umma_commit(&kv_empty[slot_of(2 * j + 1)]);
+                        release_kv(&kv_empty[slot_of(2 * j)]);
+                        release_kv(&kv_empty[slot_of(2 * j + 1)]);
                     }
                     __syncwarp();
                 }
@@ -541,10 +551,21 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     const uint32_t slot = kv_cnt % kStages;
                     mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
+                    if constexpr (kCluster > 1) {
+                        // this CTA fetches rows [64 rank, 64 rank + 64) of the tile for every CTA of the cluster
+                        // (map_k / map_v carry 64-row boxes in this mode)
+                        const int rank = (int)cluster_ctarank();
 #pragma unroll
-                    for (int hf = 0; hf < kHalves; ++hf)
-                        tma_load_4d(sKV + slot * kTileBytes + hf * kSubTileBytes, map, &kv_full[slot], hf * 64, j * kBN,
-                                    it.hk, it.b);
+                        for (int hf = 0; hf < kHalves; ++hf)
+                            tma_load_4d_multicast(sKV + slot * kTileBytes + hf * kSubTileBytes + rank * (kHN * 128), map,
+                                                  &kv_full[slot], hf * 64, j * kBN + rank * kHN, it.hk, it.b,
+                                                  (uint16_t)((1u << kCluster) - 1));
+                    } else {
+#pragma unroll
+                        for (int hf = 0; hf < kHalves; ++hf)
+                            tma_load_4d(sKV + slot * kTileBytes + hf * kSubTileBytes, map, &kv_full[slot], hf * 64, j * kBN,
+                                        it.hk, it.b);
+                    }
                     ++kv_cnt;
                 };
                 load_q(0);
@@ -562,6 +583,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
+    if constexpr (kCluster > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
     if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
@@ -661,11 +683,21 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// PLI_NO_CLUSTER=1 in the environment forces the single-CTA kernel (A/B measurements)
+bool cluster_mode_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PLI_NO_CLUSTER");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 unsigned long long* g_trace_buf = nullptr;
 int g_trace_cap = 0;
 int g_debug_flags = 0;
 
-int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int H, int B, const int64_t* st) {
+int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int H, int B, const int64_t* st,
+                int box_rows = 128) {
     EncodeTiledFn enc = get_encode_tiled();
     if (enc == nullptr) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const CUtensorMapDataType dt = dtype == PLI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -673,7 +705,7 @@ int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int
     cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
     auto fix = [&](int64_t s) -> cuuint64_t { return (cuuint64_t)(s > 0 ? s : (int64_t)D) * 2; };
     cuuint64_t strides[3] = {fix(st[2]), fix(st[1]), fix(st[0])};
-    cuuint32_t box[4] = {64, 128, 1, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -681,17 +713,29 @@ int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int
     return PLI_OK;
 }
 
-template <int kD, bool kBf16>
+template <int kD, bool kBf16, int kCluster>
 int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
              const PrefillParams& p, cudaStream_t stream) {
-    auto kern = prefill_tcgen05_kernel<kD, kBf16>;
+    auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster>;
     const int smem = SmemLayout<kD>::kTotal + 1024;
     PLI_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = sm_count();
     if (grid <= 0) grid = 148;
     if (grid > p.total_items) grid = p.total_items;
-    kern<<<grid, kThreads, smem, stream>>>(mq, mk, mv, mo, p);
-    PLI_CUDA_CHECK(cudaGetLastError());
+    if (kCluster > 1) grid -= grid % kCluster;          // total_items is a multiple of kCluster in this mode
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mo, p));
     count_launch();
     return PLI_OK;
 }
@@ -704,8 +748,11 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     CUtensorMap mq, mk, mv, mo;
     int rc;
     if ((rc = make_map_4d(&mq, q, dtype, D, Nq, Hq, B, qs))) return rc;
-    if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks))) return rc;
-    if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs))) return rc;
+    // CTA pairs share K/V when consecutive items are two q heads of one KV group (even group size): each CTA
+    // then loads 64-row halves of the K/V tiles and multicasts them
+    const bool pairs = (Hq / Hkv) % 2 == 0 && cluster_mode_enabled();
+    if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pairs ? kHN : kBN))) return rc;
+    if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pairs ? kHN : kBN))) return rc;
     if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
     PrefillParams p;
     p.lse = lse;
@@ -730,8 +777,15 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     p.trace_cap = g_trace_cap;
     p.debug_flags = g_debug_flags;
     const bool bf16 = dtype == PLI_BF16;
-    if (D == 128) return bf16 ? launch_t<128, true>(mq, mk, mv, mo, p, stream) : launch_t<128, false>(mq, mk, mv, mo, p, stream);
-    return bf16 ? launch_t<64, true>(mq, mk, mv, mo, p, stream) : launch_t<64, false>(mq, mk, mv, mo, p, stream);
+#define PLI_GO(DD, BF)                                                                            \
+    return pairs ? launch_t<DD, BF, 2>(mq, mk, mv, mo, p, stream) : launch_t<DD, BF, 1>(mq, mk, mv, mo, p, stream)
+    if (D == 128) {
+        if (bf16) PLI_GO(128, true);
+        PLI_GO(128, false);
+    }
+    if (bf16) PLI_GO(64, true);
+    PLI_GO(64, false);
+#undef PLI_GO
 }
 
 }  // namespace pli

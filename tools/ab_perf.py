@@ -27,7 +27,10 @@ print(f"burst {burst:7.1f}  sustained {sus:7.1f} TFLOP/s")
 for rep in range(2):
     for variant in sys.argv[1:]:
         env = dict(os.environ)
-        if variant:
+        if "=" in variant:                      # NAME=VALUE: same library, different environment switch
+            k_, v_ = variant.split("=", 1)
+            env[k_] = v_
+        elif variant:
             env["PLI_LIB_PATH"] = os.path.join(ROOT, "physics_llm_inference_b200", "build", f"libpli_attention_{variant}.so")
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
         print(f"[{variant or 'product':10s}] {r.stdout.strip()} {r.stderr.strip()[-200:] if r.returncode else ''}", flush=True)
