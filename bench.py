@@ -274,8 +274,23 @@ def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
         od = torch.empty(B, hq_l, D, device=dev, dtype=torch.bfloat16)
         fn = lambda: pli.flash_decode(qd, kp, vp, lens, block_tables=table, max_seq_len=L, workspace=ws, out=od)  # noqa: E731
         ms = timed(fn, 3, 20 if L < 32768 else 8)
+        # the same step as CUDA-graph replays (10 steps per graph): short contexts are launch-gap-bound otherwise
+        reps_g = 10
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            fn()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                for _ in range(reps_g):
+                    fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        ms_graph = timed(graph.replay, 1, 4 if L < 32768 else 2) / reps_g
+        del graph
         nbytes = decode_bytes(B, Hq, Hkv, L, D, bs)
         row = {"ctx": L, "us": ms * 1e3, "gbs_total": nbytes / (ms * 1e-3) / 1e9, "gbs_per_gpu": nbytes / world / (ms * 1e-3) / 1e9,
+               "graph_us": ms_graph * 1e3, "graph_gbs_per_gpu": nbytes / world / (ms_graph * 1e-3) / 1e9,
                "kv_bytes_per_gpu": 2 * pages * bs * hkv_l * D * 2, "l2_note": "single pool; >L2 except ctx 1024 at 8 GPUs"}
         if world > 1:
             row["gather_us"] = timed(lambda: pli.gather_heads(od, shard), 2, 10) * 1e3

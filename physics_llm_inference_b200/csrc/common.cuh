@@ -25,6 +25,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 int sm_count();
+int current_device();   // cached per thread; refreshed by pli_set_device
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of per launch.  Keyed by
+// the kernel's address: instantiations that share a signature must not share the flag.
+cudaError_t ensure_dynamic_smem_impl(const void* kern, int bytes);
+template <typename Kern>
+inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
+    return ensure_dynamic_smem_impl(reinterpret_cast<const void*>(kern), bytes);
+}
 
 #define PLI_CUDA_CHECK(expr)                                                                    \
     do {                                                                                        \

@@ -523,7 +523,7 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
     const size_t merge_bytes = (size_t)(128 + 64 * kD) * sizeof(float);
     size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 1024;
     if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
-    PLI_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PLI_CUDA_CHECK(ensure_dynamic_smem(kern, (int)smem));
     kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();

@@ -32,6 +32,32 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
+static thread_local int g_device = -1;
+int current_device() {
+    if (g_device < 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) g_device = dev;
+    }
+    return g_device;
+}
+
+cudaError_t ensure_dynamic_smem_impl(const void* kern, int bytes) {
+    struct Entry { const void* fn; uint64_t devices; };
+    static thread_local Entry table[64] = {};
+    const int dev = current_device();
+    Entry* slot = nullptr;
+    for (Entry& e : table) {
+        if (e.fn == kern || e.fn == nullptr) { slot = &e; break; }
+    }
+    if (slot && slot->fn == kern && dev >= 0 && dev < 64 && ((slot->devices >> dev) & 1)) return cudaSuccess;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err == cudaSuccess && slot && dev >= 0 && dev < 64) {
+        slot->fn = kern;
+        slot->devices |= 1ull << dev;
+    }
+    return err;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;
     int dev = 0;
@@ -80,6 +106,7 @@ extern "C" int pli_abi_version(void) { return PLI_ABI_VERSION; }
 extern "C" const char* pli_last_error(void) { return g_err; }
 extern "C" int pli_set_device(int device) {
     PLI_CUDA_CHECK(cudaSetDevice(device));
+    g_device = device;
     if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "CUDA device %d is not sm_100 (B200)", device);
     return PLI_OK;
 }

@@ -718,7 +718,7 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
              const PrefillParams& p, cudaStream_t stream) {
     auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster>;
     const int smem = SmemLayout<kD>::kTotal + 1024;
-    PLI_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
     int grid = sm_count();
     if (grid <= 0) grid = 148;
     if (grid > p.total_items) grid = p.total_items;

@@ -136,8 +136,7 @@ def flash_decode(
         raise RuntimeError("out must be (B, Hq, D), q's dtype, unit inner stride")
     lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
 
-    with torch.cuda.device(dev):
-        _lib.check(lib.pli_set_device(dev.index))
+    with _lib.on_device(dev):
         rc = lib.pli_decode_fwd(
             q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(), out.data_ptr(),
             lse.data_ptr() if lse is not None else None, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
@@ -191,8 +190,7 @@ def paged_gather(store: torch.Tensor, block_tables: torch.Tensor, seq_lens: torc
     _, _, bs, Hkv, D = store.shape
     out = torch.empty((B, max_len, Hkv, D), dtype=store.dtype, device=store.device)
     lib = _lib.load()
-    with torch.cuda.device(store.device):
-        _lib.check(lib.pli_set_device(store.device.index))
+    with _lib.on_device(store.device):
         rc = lib.pli_paged_gather(store.data_ptr(), out.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(), B,
                                   max_len, Hkv, D, bs, block_tables.stride(0), layer, _lib.i64(*store.stride()[:4]),
                                   _lib.dtype_code(store.dtype), _lib.current_stream_ptr(store.device))

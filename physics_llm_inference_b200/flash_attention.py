@@ -89,8 +89,7 @@ def flash_attention_forward(
     lse = torch.empty((B, Hq, Nq), dtype=torch.float32, device=q.device) if return_lse else None
 
     lib = _lib.load()
-    with torch.cuda.device(q.device):
-        _lib.check(lib.pli_set_device(q.device.index))
+    with _lib.on_device(q.device):
         rc = lib.pli_prefill_fwd(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None,
             B, Hq, Hkv, Nq, Nk, D,

@@ -60,8 +60,7 @@ def kv_append(k_store: torch.Tensor, v_store: torch.Tensor, k_new: torch.Tensor,
         st = k_store.stride()[:4]
         table_ptr, bs, tstride = block_tables.data_ptr(), k_store.shape[2], block_tables.stride(0)
     lib = _lib.load()
-    with torch.cuda.device(dev):
-        _lib.check(lib.pli_set_device(dev.index))
+    with _lib.on_device(dev):
         rc = lib.pli_kv_append(k_new.data_ptr(), v_new.data_ptr(), k_store.data_ptr(), v_store.data_ptr(), table_ptr,
                                start.data_ptr(), B, n, Hkv, D, bs, tstride, layer, _lib.i64(*k_new.stride()[:3]),
                                _lib.i64(*st), _lib.dtype_code(k_store.dtype), _lib.current_stream_ptr(dev))
