@@ -24,18 +24,11 @@ torch.cuda.synchronize()
 lib.pli_debug_prefill_trace(None, 0, 0)
 print(f"flags={flags} kernel {e0.elapsed_time(e1):.3f} ms (with tracing)")
 h = buf.cpu().tolist()
-mode = sys.argv[2] if len(sys.argv) > 2 else "events"
-for wg in range(2):
-    ph = h[3 * cap * 2 + wg * 8: 3 * cap * 2 + wg * 8 + 6]
-    if ph[5]:
-        n = ph[5]
-        print(f"softmax warp {wg * 4} phase averages over {n} tile-steps: wait_S {ph[0] / n:.0f} ld {ph[1] / n:.0f} max+xchg {ph[2] / n:.0f} "
-              f"exp+st {ph[3] / n:.0f} post {ph[4] / n:.0f} | sum {sum(ph[:5]) / n:.0f}")
-recs = [(h[2 * i + 1], h[2 * i] & 0xFF, (h[2 * i] >> 8) & 0xFF, (h[2 * i] >> 16) & 0xFFFF) for i in range(3 * cap) if h[2 * i] >> 40]
+recs = [(h[2 * i + 1], h[2 * i] & 0xFF, (h[2 * i] >> 8) & 0xFF, (h[2 * i] >> 16) & 0xFFFF) for i in range(4 * cap) if h[2 * i] >> 40]
 recs.sort()
 t0 = recs[0][0]
 names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "mma: V landed", 7: "mma: O corrected", 8: "mma: P seen"}
-print("first item (64 KV tiles for tile 1): events of steps 20..23")
+print("first item: events of half-steps 40..44 (regions: softmax tile 0/1, MMA warp of tile 0/1)")
 for clk, ev, t, j in recs:
     if 40 <= j <= 44 and clk - t0 < 800000:
         print(f"  {clk - t0:8d}  tile{t} j={j:3d} {names[ev]}")
