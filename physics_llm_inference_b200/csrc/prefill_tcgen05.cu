@@ -62,8 +62,11 @@ struct SmemLayout {
 struct PrefillParams {
     float* lse;
     int B, Hq, Hkv, Nq, Nk;
-    int num_pairs;        // ceil(Nq / 256)
-    int total_items;      // B * Hq * num_pairs
+    int num_pairs;        // row slots per head: ceil(Nq / 256) (row-pair items) or ceil(Nq / 128) (head-pair items)
+    int total_items;      // B * Hq * num_pairs (row pairs) or B * Hq / 2 * num_pairs (head pairs)
+    int head_pairs;       // 1: the two Q tiles of an item are the SAME 128 rows of two adjacent q heads of one KV
+                          //    group (even group size): equal trip counts, no dead second tile for short Nq;
+                          // 0: two consecutive 128-row blocks of one head
     int causal;
     float scale_log2;     // scale * log2(e)
     float scale;
@@ -99,7 +102,8 @@ __device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& 
 }
 
 struct WorkItem {
-    int b, h, hk, q0;     // q0 = first row of Q tile 0; tile 1 starts at q0 + 128
+    int b, hk;            // batch, kv head
+    int q0[2], h[2];      // first row and q head of Q tile 0 / 1
     int n[2];             // 64-key half-steps per Q tile (n[1] >= n[0])
     int n_kv;             // 128-key K/V tiles to load
 };
@@ -114,28 +118,37 @@ __device__ __forceinline__ int item_of_round(int i, const PrefillParams& p) {
 }
 
 __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
-    // Longest first, in blocks of p.pair_block consecutive tile-pair indices.  Inside a block the order is
-    // KV group (batch, kv head) -> pair -> q head of the group, so the ~148 items in flight share few KV
-    // groups and their K/V stay L2-resident (modelled DRAM K/V traffic on C2: 1.9 GB for blocks of 1, 1.2 GB
-    // for 2, 0.65 GB for 4; measured +2 % throughput for 2 and 4 over 1); item sizes inside a block differ by
-    // < pair_block tiles, so the snake schedule still balances (C2: 0.3 % / 0.3 % / 1.2 % for 1 / 2 / 4).
-    const int kPairBlock = p.pair_block;
+    // Longest first, in blocks of p.pair_block consecutive row slots.  Inside a block the order is
+    // KV group (batch, kv head) -> slot -> item of the group (q head, or pair of q heads), so the ~148 items in
+    // flight share few KV groups and their K/V stay L2-resident (modelled DRAM K/V traffic on C2: 1.9 GB for
+    // blocks of 1, 1.2 GB for 2, 0.65 GB for 4; measured +2 %); item sizes inside a block differ by
+    // < pair_block slots, so the snake schedule still balances.  Consecutive items (even, odd) are the same
+    // slot of the same KV group whenever the per-group item count is even: that is what CTA pairs rely on.
     WorkItem it;
+    const int kPairBlock = p.pair_block;
     const int G = p.Hq / p.Hkv;
-    const int bh = p.B * p.Hq;
-    const int blk = w / (kPairBlock * bh);
-    int r = w - blk * kPairBlock * bh;
-    const int top = p.num_pairs - 1 - blk * kPairBlock;           // largest pair index of this block
-    const int cnt = min(kPairBlock, top + 1);                      // pairs in this block (the last one may be short)
-    const int g = r / (cnt * G);
-    r -= g * cnt * G;
-    const int pair = top - r / G;
+    const int Gi = p.head_pairs ? G / 2 : G;                       // items per (KV group, slot)
+    const int per_slot = p.B * p.Hkv * Gi;
+    const int blk = w / (kPairBlock * per_slot);
+    int r = w - blk * kPairBlock * per_slot;
+    const int top = p.num_pairs - 1 - blk * kPairBlock;           // largest slot index of this block
+    const int cnt = min(kPairBlock, top + 1);                      // slots in this block (the last one may be short)
+    const int g = r / (cnt * Gi);
+    r -= g * cnt * Gi;
+    const int slot = top - r / Gi;
     it.b = g / p.Hkv;
     it.hk = g % p.Hkv;
-    it.h = it.hk * G + r % G;
-    it.q0 = pair * 2 * kBM;
-    it.n[0] = half_steps_for(it.q0, p);
-    it.n[1] = half_steps_for(it.q0 + kBM, p);
+    if (p.head_pairs) {
+        it.h[0] = it.hk * G + (r % Gi) * 2;
+        it.h[1] = it.h[0] + 1;
+        it.q0[0] = it.q0[1] = slot * kBM;
+    } else {
+        it.h[0] = it.h[1] = it.hk * G + r % Gi;
+        it.q0[0] = slot * 2 * kBM;
+        it.q0[1] = it.q0[0] + kBM;
+    }
+    it.n[0] = half_steps_for(it.q0[0], p);
+    it.n[1] = half_steps_for(it.q0[1], p);
     if (it.n[1] < it.n[0]) it.n[1] = it.n[0];
     it.n_kv = (it.n[1] + 1) >> 1;
     return it;
@@ -238,7 +251,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd) {
             const uint32_t item_par = rnd & 1;
             const WorkItem it = decode_item(w, p);
-            const int q_tile0 = it.q0 + t * kBM;
+            const int q_tile0 = it.q0[t];
             const int q_row = q_tile0 + row;
             const int nt = it.n[t];
             float m_ref = -INFINITY;                      // reference max (raw score units)
@@ -383,7 +396,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stats_free[t]);
                 const float inv = 1.f / dsum;
-                const int q_tile0 = it.q0 + t * kBM;
+                const int q_tile0 = it.q0[t];
 #pragma unroll
                 for (int hf = 0; hf < kHalves; ++hf) {
                     // the previous TMA store must have finished reading sO before it is overwritten
@@ -416,12 +429,12 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     fence_proxy_async();
                     named_bar_sync(kBarEpilogue, 128);
                     if (warp == 8 && lane == 0 && q_tile0 < p.Nq) {
-                        tma_store_4d(&map_o, sO, hf * 64, q_tile0, it.h, it.b);
+                        tma_store_4d(&map_o, sO, hf * 64, q_tile0, it.h[t], it.b);
                         tma_store_commit();
                     }
                 }
                 if (p.lse != nullptr && q_tile0 + row < p.Nq)
-                    p.lse[((int64_t)it.b * p.Hq + it.h) * p.Nq + q_tile0 + row] = (mlog2 + log2f(dsum)) * kLn2;
+                    p.lse[((int64_t)it.b * p.Hq + it.h[t]) * p.Nq + q_tile0 + row] = (mlog2 + log2f(dsum)) * kLn2;
                 // s_full[t*2+h] completed ceil((n_t - h) / 2) phases in this item
                 sf_base ^= (uint32_t)(((it.n[t] + 1) >> 1) & 1) << (t * 2);
                 sf_base ^= (uint32_t)((it.n[t] >> 1) & 1) << (t * 2 + 1);
@@ -545,7 +558,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
                     for (int hf = 0; hf < kHalves; ++hf)
                         tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
-                                    it.q0 + t * kBM, it.h, it.b);
+                                    it.q0[t], it.h[t], it.b);
                 };
                 auto load_kv = [&](const CUtensorMap* map, int j) {
                     const uint32_t slot = kv_cnt % kStages;
@@ -750,7 +763,9 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     if ((rc = make_map_4d(&mq, q, dtype, D, Nq, Hq, B, qs))) return rc;
     // CTA pairs share K/V when consecutive items are two q heads of one KV group (even group size): each CTA
     // then loads 64-row halves of the K/V tiles and multicasts them
-    const bool pairs = (Hq / Hkv) % 2 == 0 && cluster_mode_enabled();
+    // (even, odd) items share their K/V when the per-group item count is even: group size divisible by 4 with
+    // head-pair items (group size odd -> row-pair items of single heads -> never)
+    const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
     if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pairs ? kHN : kBN))) return rc;
     if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pairs ? kHN : kBN))) return rc;
     if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
@@ -761,8 +776,10 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     p.Hkv = Hkv;
     p.Nq = Nq;
     p.Nk = Nk;
-    p.num_pairs = (Nq + 2 * kBM - 1) / (2 * kBM);
-    const int64_t total = (int64_t)B * Hq * p.num_pairs;
+    const int group = Hq / Hkv;
+    p.head_pairs = group % 2 == 0 ? 1 : 0;
+    p.num_pairs = p.head_pairs ? (Nq + kBM - 1) / kBM : (Nq + 2 * kBM - 1) / (2 * kBM);
+    const int64_t total = (int64_t)B * (p.head_pairs ? Hq / 2 : Hq) * p.num_pairs;
     if (total > 0x7fffffff) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
     p.total_items = (int)total;
     p.causal = causal;
@@ -770,7 +787,7 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     p.scale_log2 = scale * kLog2e;
     {   // 4 when every CTA gets many items (the balance cost of a block amortises), else 2, never more than num_pairs
         int grid = sm_count() > 0 ? sm_count() : 148;
-        p.pair_block = total >= (int64_t)16 * grid ? 4 : 2;
+        p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);   // in 128- or 256-row slots
         if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
     }
     p.trace = g_trace_buf;
