@@ -84,6 +84,23 @@ int pli_prefill_fwd(const void* q, const void* k, const void* v, void* o, float*
                     const int64_t v_strides[3], const int64_t o_strides[3],
                     float scale, int causal, int dtype, void* stream);
 
+/* Chunked prefill over PAGED K/V: Nq new query tokens per sequence attend to that sequence's
+ * cached keys, read in place from the ch07 pools (ch07/paged_memory.py:38-48) through the block table — what
+ * `ChunkedPrefillScheduler` (ch08/chunked_prefill.py:32-51,79-113) emits once the chunk's own K/V have been
+ * appended (pli_kv_append).  Maths: ch02/cached_generation.py:72-94 with the offset causal mask :85-91,
+ * per sequence: query i sees key j iff j <= i + (seq_lens[b] - Nq); requires seq_lens[b] >= Nq.
+ *   q, o (B,Hq,Nq,D) strides {batch, head, token};  pools / block_table / kv_strides / layer as for decode;
+ *   seq_lens (B,) int32 device: cached length of each sequence INCLUDING the Nq new tokens;
+ *   max_seq_len: host upper bound;  bf16/f16, D in {64,128}, block_size in {16,32,64,128}.
+ * Slots of a sequence's last page past seq_lens[b] are read (and masked): they must hold finite values, which
+ * the reference's zero-initialised pools (ch07/paged_memory.py:44-47) guarantee. */
+int pli_prefill_paged_fwd(const void* q, const void* k_pool, const void* v_pool,
+                          const int32_t* block_table, const int32_t* seq_lens, void* o, float* lse,
+                          int B, int Hq, int Hkv, int Nq, int D, int max_seq_len,
+                          int block_size, int table_stride, int layer, int64_t num_pages,
+                          const int64_t q_strides[3], const int64_t kv_strides[4], const int64_t o_strides[3],
+                          float scale, int dtype, void* stream);
+
 /* Which kernel pli_prefill_fwd would use for this problem (PLI_KIND_*), without launching. */
 int pli_prefill_kernel_kind(int D, int dtype, const int64_t q_strides[3], const int64_t k_strides[3],
                             const int64_t v_strides[3], const int64_t o_strides[3],

@@ -4,7 +4,7 @@ Drop-in surface (same names and call signatures as the reference packages it rep
 
   ch06  flash_attention_forward, FlashAttentionConfig, attention_flops, flash_attention_memory_bytes
   ch02  KVCache, LayerKVCache, create_caches            (+ flash_decode / decode_with_cache)
-  ch07  BlockTable, PagedKVCache                        (+ decode_with_paged, kv_append)
+  ch07  BlockTable, PagedKVCache                        (+ decode_with_paged, prefill_with_paged, kv_append)
 
 Everything numeric runs in `libpli_attention.so` (hand-written sm_100a CUDA behind the C ABI in
 include/pli_attention.h).  Importing the package does not need a GPU; calling an op does, and
@@ -12,19 +12,20 @@ fails loudly if the library has not been built.
 """
 from ._lib import LIB_PATH, PliError, launch_count, reset_launch_count
 from .decode import (decode_kernel_kind, decode_num_splits, decode_with_cache, decode_with_paged, decode_workspace,
-                     flash_decode, paged_gather)
+                     flash_decode, paged_gather, prefill_with_paged)
 from .flash_attention import (FlashAttentionConfig, attention_flops, flash_attention, flash_attention_forward,
-                              flash_attention_memory_bytes, prefill_algorithmic_flops, prefill_kernel_kind)
+                              flash_attention_memory_bytes, flash_attention_paged, prefill_algorithmic_flops,
+                              prefill_kernel_kind)
 from .kv_cache import KVCache, LayerKVCache, create_caches, kv_append
 from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention
 from .paged_memory import BlockTable, PagedKVCache
 from .sharding import HeadShard, gather_heads, init_distributed, make_shard, shard_kv_heads
 
 __all__ = [
-    "flash_attention_forward", "flash_attention", "FlashAttentionConfig", "attention_flops",
+    "flash_attention_forward", "flash_attention", "flash_attention_paged", "FlashAttentionConfig", "attention_flops",
     "flash_attention_memory_bytes", "prefill_algorithmic_flops", "prefill_kernel_kind",
     "flash_decode", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
-    "decode_kernel_kind", "paged_gather",
+    "decode_kernel_kind", "paged_gather", "prefill_with_paged",
     "KVCache", "LayerKVCache", "create_caches", "kv_append", "BlockTable", "PagedKVCache",
     "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner",
     "HeadShard", "make_shard", "shard_kv_heads", "gather_heads", "init_distributed",

@@ -52,6 +52,11 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
                            int Hkv, int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks,
                            const int64_t* vs, const int64_t* os, float scale, int causal, int dtype,
                            cudaStream_t stream);
+int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table,
+                                 const int32_t* seq_lens, void* o, float* lse, int B, int Hq, int Hkv, int Nq, int D,
+                                 int max_seq_len, int block_size, int table_stride, int layer, int64_t num_pages,
+                                 const int64_t* qs, const int64_t* kvs, const int64_t* os, float scale, int dtype,
+                                 cudaStream_t stream);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
@@ -162,6 +167,15 @@ __device__ __forceinline__ void tma_load_4d_multicast(void* smem_dst, const CUte
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
         " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_multicast(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                                      int c1, int c2, int c3, int c4, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+        "h"(cta_mask)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1,

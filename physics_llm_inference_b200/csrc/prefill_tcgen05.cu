@@ -75,6 +75,11 @@ struct PrefillParams {
     int trace_cap;
     int debug_flags;             // bit 0: skip the exp2 / P computation (timing experiments only)
     int pair_block;              // scheduling block (see decode_item)
+    // paged K/V (kPaged kernels): keys of sequence b come from the pools through its block-table row; Nk is then
+    // per sequence (seq_lens[b]) and the mask is bottom-right aligned per sequence
+    const int32_t* table;
+    const int32_t* seq_lens;
+    int table_stride, page_size, layer, box_rows;
 };
 
 // CTA 0 timeline: each tracing warp owns region `region` of the buffer and keeps its own cursor in a
@@ -93,10 +98,10 @@ __device__ __forceinline__ void trace_event(const PrefillParams& p, int lane, in
 
 constexpr int kHN = 64;                // keys per softmax / MMA half-step (half of a KV tile)
 
-__device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& p) {
+__device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& p, int nk) {
     // number of 64-key half-steps a Q tile starting at row q0_tile attends to (>= 1)
-    int kmax = p.Nk;
-    if (p.causal) kmax = min(p.Nk, q0_tile + kBM + (p.Nk - p.Nq));
+    int kmax = nk;
+    if (p.causal) kmax = min(nk, q0_tile + kBM + (nk - p.Nq));
     kmax = max(kmax, 1);
     return (kmax + kHN - 1) / kHN;
 }
@@ -106,6 +111,7 @@ struct WorkItem {
     int q0[2], h[2];      // first row and q head of Q tile 0 / 1
     int n[2];             // 64-key half-steps per Q tile (n[1] >= n[0])
     int n_kv;             // 128-key K/V tiles to load
+    int nk;               // keys of this item's sequence (p.Nk, or seq_lens[b] with paged K/V)
 };
 
 // Static persistent schedule, longest item first.  Round i hands items [i*G, (i+1)*G) to the G CTAs, in
@@ -147,8 +153,9 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
         it.q0[0] = slot * 2 * kBM;
         it.q0[1] = it.q0[0] + kBM;
     }
-    it.n[0] = half_steps_for(it.q0[0], p);
-    it.n[1] = half_steps_for(it.q0[1], p);
+    it.nk = p.seq_lens != nullptr ? p.seq_lens[it.b] : p.Nk;
+    it.n[0] = half_steps_for(it.q0[0], p, it.nk);
+    it.n[1] = half_steps_for(it.q0[1], p, it.nk);
     if (it.n[1] < it.n[0]) it.n[1] = it.n[0];
     it.n_kv = (it.n[1] + 1) >> 1;
     return it;
@@ -158,7 +165,9 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
 // the same Q-tile pair, so they need the same K/V tiles: each CTA TMA-loads half of every tile and MULTICASTS it
 // into both CTAs' shared memory (L2 -> SM traffic of K/V halves), and a ring slot is refilled once the MMA warps
 // of both CTAs have released it (tcgen05.commit multicast onto both CTAs' kv_empty barriers).
-template <int kD, bool kBf16, int kCluster>
+// kPaged: K/V tiles are assembled from block-table pages (one TMA box per page / half page, issued by the lanes of
+// the producer warp) instead of one box per tile; everything downstream of shared memory is identical.
+template <int kD, bool kBf16, int kCluster, bool kPaged>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
@@ -245,7 +254,6 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int row = (warp & 3) * 32 + lane;           // row inside the tile == TMEM lane
         const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
         const float c = p.scale_log2;
-        const int off = p.Nk - p.Nq;
         uint32_t sf_par = 0;                              // bit h: phase parity of s_full[t*2+h]
         int trace_cur = 0;
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd) {
@@ -253,6 +261,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const WorkItem it = decode_item(w, p);
             const int q_tile0 = it.q0[t];
             const int q_row = q_tile0 + row;
+            const int nk = it.nk, off = it.nk - p.Nq;
             const int nt = it.n[t];
             float m_ref = -INFINITY;                      // reference max (raw score units)
             float d = 0.f;                                // running row sum relative to m_ref
@@ -269,9 +278,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tc_wait_ld();
                 // mask: key padding and the causal diagonal (warp-uniform test, per-row limit)
                 const int k0 = s * kHN;
-                const bool need_mask = (k0 + kHN > p.Nk) || (p.causal && (k0 + kHN - 1 > q_tile0 + off));
+                const bool need_mask = (k0 + kHN > nk) || (p.causal && (k0 + kHN - 1 > q_tile0 + off));
                 if (need_mask) {
-                    int vis = p.Nk - 1 - k0;
+                    int vis = nk - 1 - k0;
                     if (p.causal) vis = min(vis, q_row + off - k0);
 #pragma unroll
                     for (int i = 0; i < 64; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
@@ -543,36 +552,65 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 kv_cnt += 2 * it.n_kv;
             }
-        } else if (warp == 14 && lane == 0) {
+        } else if (warp == 14 && (kPaged || lane == 0)) {
             // =========================== TMA producer ===========================
-            prefetch_tensormap(&map_q);
-            prefetch_tensormap(&map_k);
-            prefetch_tensormap(&map_v);
-            prefetch_tensormap(&map_o);
+            if (lane == 0) {
+                prefetch_tensormap(&map_q);
+                prefetch_tensormap(&map_k);
+                prefetch_tensormap(&map_v);
+                prefetch_tensormap(&map_o);
+            }
             uint32_t kv_cnt = 0, item_par = 0;
+            const int rank = kCluster > 1 ? (int)cluster_ctarank() : 0;
+            const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
             for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
                 auto load_q = [&](int t) {
-                    mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
-                    mbar_arrive_expect_tx(&q_full[t], kTileBytes);
+                    if (lane == 0) {
+                        mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
+                        mbar_arrive_expect_tx(&q_full[t], kTileBytes);
 #pragma unroll
-                    for (int hf = 0; hf < kHalves; ++hf)
-                        tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
-                                    it.q0[t], it.h[t], it.b);
+                        for (int hf = 0; hf < kHalves; ++hf)
+                            tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
+                                        it.q0[t], it.h[t], it.b);
+                    }
                 };
-                auto load_kv = [&](const CUtensorMap* map, int j) {
+                // paged: this lane's box of every K/V tile covers tile rows [row0, row0 + box_rows); its page id is
+                // looked up once per tile j (K and V share it).  Boxes past the sequence end re-read the last valid
+                // page (the byte count per tile stays fixed; those keys are masked).
+                const int rows_cta = kBN / kCluster;
+                const int n_boxes = kPaged ? rows_cta / p.box_rows : 0;
+                const int row0 = rank * rows_cta + lane * p.box_rows;
+                auto page_of = [&](int j) -> int {
+                    if (!kPaged || lane >= n_boxes) return 0;
+                    const int key = min(j * kBN + row0, it.nk - 1);
+                    return p.table[(int64_t)it.b * p.table_stride + key / p.page_size];
+                };
+                auto load_kv = [&](const CUtensorMap* map, int j, int page) {
                     const uint32_t slot = kv_cnt % kStages;
                     mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
-                    if constexpr (kCluster > 1) {
+                    if (lane == 0) mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
+                    if constexpr (kPaged) {
+                        __syncwarp();
+                        if (lane < n_boxes) {
+                            const int in_page = min(j * kBN + row0, it.nk - 1) % p.page_size;
+                            const int slot0 = in_page - in_page % p.box_rows;      // box-aligned slot inside the page
+#pragma unroll
+                            for (int hf = 0; hf < kHalves; ++hf) {
+                                uint8_t* dst = sKV + slot * kTileBytes + hf * kSubTileBytes + row0 * 128;
+                                if constexpr (kCluster > 1)
+                                    tma_load_5d_multicast(dst, map, &kv_full[slot], hf * 64, it.hk, slot0, p.layer, page, cmask);
+                                else
+                                    tma_load_5d(dst, map, &kv_full[slot], hf * 64, it.hk, slot0, p.layer, page);
+                            }
+                        }
+                    } else if constexpr (kCluster > 1) {
                         // this CTA fetches rows [64 rank, 64 rank + 64) of the tile for every CTA of the cluster
                         // (map_k / map_v carry 64-row boxes in this mode)
-                        const int rank = (int)cluster_ctarank();
 #pragma unroll
                         for (int hf = 0; hf < kHalves; ++hf)
                             tma_load_4d_multicast(sKV + slot * kTileBytes + hf * kSubTileBytes + rank * (kHN * 128), map,
-                                                  &kv_full[slot], hf * 64, j * kBN + rank * kHN, it.hk, it.b,
-                                                  (uint16_t)((1u << kCluster) - 1));
+                                                  &kv_full[slot], hf * 64, j * kBN + rank * kHN, it.hk, it.b, cmask);
                     } else {
 #pragma unroll
                         for (int hf = 0; hf < kHalves; ++hf)
@@ -581,13 +619,15 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     }
                     ++kv_cnt;
                 };
+                int page = page_of(0);
                 load_q(0);
-                load_kv(&map_k, 0);
+                load_kv(&map_k, 0, page);
                 load_q(1);
-                load_kv(&map_v, 0);
+                load_kv(&map_v, 0, page);
                 for (int j = 1; j < it.n_kv; ++j) {
-                    load_kv(&map_k, j);
-                    load_kv(&map_v, j);
+                    page = page_of(j);
+                    load_kv(&map_k, j, page);
+                    load_kv(&map_v, j, page);
                 }
             }
         }
@@ -726,10 +766,10 @@ int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int
     return PLI_OK;
 }
 
-template <int kD, bool kBf16, int kCluster>
+template <int kD, bool kBf16, int kCluster, bool kPaged = false>
 int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
              const PrefillParams& p, cudaStream_t stream) {
-    auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster>;
+    auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster, kPaged>;
     const int smem = SmemLayout<kD>::kTotal + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
     int grid = sm_count();
@@ -753,7 +793,86 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
     return PLI_OK;
 }
 
+// 5-D map over a paged pool (num_pages, layers, page_size, Hkv, D): dims fastest first d, head, slot, layer, page
+int make_pool_map(CUtensorMap* map, const void* base, int dtype, int D, int Hkv, int page_size, int layers, int64_t pages,
+                  const int64_t* st, int box_rows) {
+    EncodeTiledFn enc = get_encode_tiled();
+    if (enc == nullptr) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const CUtensorMapDataType dt = dtype == PLI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[5] = {(cuuint64_t)D, (cuuint64_t)Hkv, (cuuint64_t)page_size, (cuuint64_t)layers, (cuuint64_t)pages};
+    const int64_t layer_stride = st[1] > 0 ? st[1] : st[0];
+    cuuint64_t strides[4] = {(cuuint64_t)st[3] * 2, (cuuint64_t)st[2] * 2, (cuuint64_t)layer_stride * 2, (cuuint64_t)st[0] * 2};
+    cuuint32_t box[5] = {64, 1, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(map, dt, 5, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled(pool) failed with CUresult %d", (int)r);
+    return PLI_OK;
+}
+
+void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
+    const int group = Hq / Hkv;
+    p.head_pairs = group % 2 == 0 ? 1 : 0;
+    p.num_pairs = p.head_pairs ? (Nq + kBM - 1) / kBM : (Nq + 2 * kBM - 1) / (2 * kBM);
+    const int64_t total = (int64_t)B * (p.head_pairs ? Hq / 2 : Hq) * p.num_pairs;
+    p.total_items = total > 0x7fffffff ? -1 : (int)total;
+    // 4 when every CTA gets many items (the balance cost of a block amortises), else 2, never more than num_pairs
+    int grid = sm_count() > 0 ? sm_count() : 148;
+    p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);   // in 128- or 256-row slots
+    if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
+    p.trace = g_trace_buf;
+    p.trace_cap = g_trace_cap;
+    p.debug_flags = g_debug_flags;
+    p.table = nullptr;
+    p.seq_lens = nullptr;
+    p.table_stride = p.page_size = p.layer = p.box_rows = 0;
+}
+
 }  // namespace
+
+int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table,
+                                 const int32_t* seq_lens, void* o, float* lse, int B, int Hq, int Hkv, int Nq, int D,
+                                 int max_seq_len, int block_size, int table_stride, int layer, int64_t num_pages,
+                                 const int64_t* qs, const int64_t* kvs, const int64_t* os, float scale, int dtype,
+                                 cudaStream_t stream) {
+    const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
+    const int rows_cta = pairs ? kHN : kBN;
+    const int box_rows = block_size < rows_cta ? block_size : rows_cta;
+    CUtensorMap mq, mk, mv, mo;
+    int rc;
+    if ((rc = make_map_4d(&mq, q, dtype, D, Nq, Hq, B, qs))) return rc;
+    if ((rc = make_pool_map(&mk, k_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
+    if ((rc = make_pool_map(&mv, v_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
+    if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
+    PrefillParams p;
+    p.lse = lse;
+    p.B = B;
+    p.Hq = Hq;
+    p.Hkv = Hkv;
+    p.Nq = Nq;
+    p.Nk = max_seq_len;
+    p.causal = 1;
+    p.scale = scale;
+    p.scale_log2 = scale * kLog2e;
+    fill_schedule(p, B, Hq, Hkv, Nq);
+    if (p.total_items < 0) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
+    p.table = block_table;
+    p.seq_lens = seq_lens;
+    p.table_stride = table_stride;
+    p.page_size = block_size;
+    p.layer = layer;
+    p.box_rows = box_rows;
+    const bool bf16 = dtype == PLI_BF16;
+#define PLI_GO(DD, BF)                                                                                  \
+    return pairs ? launch_t<DD, BF, 2, true>(mq, mk, mv, mo, p, stream) : launch_t<DD, BF, 1, true>(mq, mk, mv, mo, p, stream)
+    if (D == 128) {
+        if (bf16) PLI_GO(128, true);
+        PLI_GO(128, false);
+    }
+    if (bf16) PLI_GO(64, true);
+    PLI_GO(64, false);
+#undef PLI_GO
+}
 
 int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv,
                            int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks, const int64_t* vs,
@@ -776,23 +895,11 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     p.Hkv = Hkv;
     p.Nq = Nq;
     p.Nk = Nk;
-    const int group = Hq / Hkv;
-    p.head_pairs = group % 2 == 0 ? 1 : 0;
-    p.num_pairs = p.head_pairs ? (Nq + kBM - 1) / kBM : (Nq + 2 * kBM - 1) / (2 * kBM);
-    const int64_t total = (int64_t)B * (p.head_pairs ? Hq / 2 : Hq) * p.num_pairs;
-    if (total > 0x7fffffff) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
-    p.total_items = (int)total;
     p.causal = causal;
     p.scale = scale;
     p.scale_log2 = scale * kLog2e;
-    {   // 4 when every CTA gets many items (the balance cost of a block amortises), else 2, never more than num_pairs
-        int grid = sm_count() > 0 ? sm_count() : 148;
-        p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);   // in 128- or 256-row slots
-        if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
-    }
-    p.trace = g_trace_buf;
-    p.trace_cap = g_trace_cap;
-    p.debug_flags = g_debug_flags;
+    fill_schedule(p, B, Hq, Hkv, Nq);
+    if (p.total_items < 0) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
     const bool bf16 = dtype == PLI_BF16;
 #define PLI_GO(DD, BF)                                                                            \
     return pairs ? launch_t<DD, BF, 2>(mq, mk, mv, mo, p, stream) : launch_t<DD, BF, 1>(mq, mk, mv, mo, p, stream)

@@ -180,6 +180,17 @@ def decode_with_paged(q: torch.Tensor, paged: PagedKVCache, request_ids, *, laye
     return flash_decode(q, paged.k_cache, paged.v_cache, lens, block_tables=bt, layer=layer, max_seq_len=max_len, **kw)
 
 
+def prefill_with_paged(q: torch.Tensor, paged: PagedKVCache, request_ids, *, layer: int = 0, **kw):
+    """Chunked prefill (q (B, Hq, Nq, D), Nq >= 1 newest tokens) over a `PagedKVCache` for the given request ids:
+    `flash_attention_paged` with the block tables / lengths taken from the allocator mirror."""
+    from .flash_attention import flash_attention_paged
+    if paged.k_cache is None:
+        raise RuntimeError("PagedKVCache has no device pools (constructed without CUDA)")
+    bt, lens = paged.block_table_tensor(request_ids, device=q.device)
+    max_len = max(paged.block_tables[r].num_tokens for r in request_ids)
+    return flash_attention_paged(q, paged.k_cache, paged.v_cache, bt, lens, layer=layer, max_seq_len=max_len, **kw)
+
+
 def paged_gather(store: torch.Tensor, block_tables: torch.Tensor, seq_lens: torch.Tensor, max_len: int,
                  layer: int = 0) -> torch.Tensor:
     """Gather one layer of a paged pool to (B, max_len, Hkv, D) with the kernels' address rule

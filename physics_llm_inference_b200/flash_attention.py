@@ -146,3 +146,57 @@ def prefill_algorithmic_flops(B: int, Hq: int, Nq: int, Nk: int, D: int, causal:
     block plus half of the Nq x Nq triangle."""
     pairs = Nq * Nk if not causal else Nq * (Nk - Nq) + Nq * Nq / 2
     return 4.0 * B * Hq * D * pairs
+
+
+def flash_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_tables: torch.Tensor,
+                          seq_lens: torch.Tensor, *, layer: int = 0, scale: float | None = None,
+                          max_seq_len: int | None = None, return_lse: bool = False):
+    """Chunked prefill over the ch07 paged pools, read in place (no gather).
+
+    q (B, Hq, Nq, D): the Nq newest tokens of each sequence (their K/V already appended to the pools, e.g. with
+    `PagedKVCache.append`); pools (P, layers, bs, Hkv, D); block_tables (B, max_pages) int32; seq_lens (B,) int32
+    CUDA = cached length per sequence including the chunk.  Query i of sequence b sees key j iff
+    j <= i + (seq_lens[b] - Nq): the offset mask of ch02/cached_generation.py:85-91, per sequence.
+    Returns o like q (and lse (B, Hq, Nq) float32 when return_lse).
+    """
+    if not (q.is_cuda and k_pool.is_cuda and v_pool.is_cuda):
+        raise RuntimeError("flash_attention_paged runs on CUDA tensors only (no CPU fallback)")
+    if q.dim() != 4 or k_pool.dim() != 5:
+        raise RuntimeError(f"q must be (B, Hq, Nq, D) and the pools (P, layers, bs, Hkv, D); got {tuple(q.shape)}, {tuple(k_pool.shape)}")
+    if not (q.dtype == k_pool.dtype == v_pool.dtype):
+        raise RuntimeError("q and the pools must share a dtype")
+    if k_pool.shape != v_pool.shape or k_pool.stride() != v_pool.stride() or k_pool.stride(-1) != 1:
+        raise RuntimeError("k and v pools must have the same shape/strides and a unit head_dim stride")
+    B, Hq, Nq, D = q.shape
+    P, n_layers, bs, Hkv, Dk = k_pool.shape
+    if Dk != D or Hq % Hkv != 0:
+        raise RuntimeError(f"pools {tuple(k_pool.shape)} do not match q {tuple(q.shape)}")
+    if not 0 <= layer < n_layers:
+        raise IndexError(f"layer {layer} out of range for {n_layers} layers")
+    if block_tables.dtype != torch.int32 or not block_tables.is_cuda or block_tables.dim() != 2 or block_tables.shape[0] != B:
+        raise RuntimeError("block_tables must be a (B, max_pages) CUDA int32 tensor")
+    if seq_lens.dtype != torch.int32 or not seq_lens.is_cuda or seq_lens.shape != (B,):
+        raise RuntimeError("seq_lens must be a (B,) CUDA int32 tensor")
+    if block_tables.stride(-1) != 1:
+        block_tables = block_tables.contiguous()
+    seq_lens = seq_lens.contiguous()
+    q = _unit_inner(q)
+    cap = block_tables.shape[1] * bs
+    max_seq_len = cap if max_seq_len is None else min(int(max_seq_len), cap)
+    if Nq > max_seq_len:
+        raise ValueError(f"Nq ({Nq}) exceeds the cached length bound ({max_seq_len})")
+    if scale is None:
+        scale = D ** -0.5
+    out = torch.empty_like(q)
+    if out.stride(-1) != 1:
+        out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, Hq, Nq), dtype=torch.float32, device=q.device) if return_lse else None
+    lib = _lib.load()
+    with _lib.on_device(q.device):
+        rc = lib.pli_prefill_paged_fwd(
+            q.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
+            out.data_ptr(), lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Nq, D, max_seq_len, bs,
+            block_tables.stride(0), layer, P, _lib.i64(*q.stride()[:3]), _lib.i64(*k_pool.stride()[:4]),
+            _lib.i64(*out.stride()[:3]), float(scale), _lib.dtype_code(q.dtype), _lib.current_stream_ptr(q.device))
+    _lib.check(rc)
+    return (out, lse) if return_lse else out

@@ -217,3 +217,52 @@ def test_prefill_is_deterministic_and_race_free(shape, causal):
     for _ in range(25):
         o, l = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
         assert torch.equal(o, o0) and torch.equal(l, l0)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("bs,D,Hkv,G,Nq,lens", [
+    (16, 128, 2, 4, 128, [512, 300, 128]),          # C3-style pages, cluster pairs (G % 4 == 0), ragged cache lengths
+    (16, 128, 1, 2, 200, [777, 200]),               # head pairs without cluster, ragged Nq tile
+    (64, 64, 2, 1, 96, [1000, 97, 640]),            # MHA: row-pair items, big pages, D 64
+    (128, 128, 2, 8, 256, [1500, 256]),
+    (32, 128, 1, 4, 1, [33, 1, 64]),                # single new token through the prefill kernel
+])
+def test_paged_prefill_parity(bs, D, Hkv, G, Nq, lens, dtype):
+    """Chunked prefill over the paged pools in place == oracle (page gather + ch02 maths with the offset mask)."""
+    B, Hq = len(lens), Hkv * G
+    _, kp, vp, table, lens_t = orc.seeded_paged(61, B, Hq, Hkv, D, bs, lens, num_layers=2, dtype=dtype)
+    g = torch.Generator().manual_seed(62)
+    q = torch.randn(B, Hq, Nq, D, generator=g).to(dtype)
+    o, lse = pli.flash_attention_paged(q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens_t.cuda(), layer=1,
+                                       return_lse=True, max_seq_len=max(lens))
+    ro, rlse = orc.paged_decode_oracle(q, kp, vp, table, lens_t, layer=1)
+    assert (o.float().cpu() - ro).abs().max().item() <= 2e-2
+    assert (lse.cpu() - rlse).abs().max().item() <= 1e-3
+    # and the same arithmetic as gathering the pages first and calling the contiguous kernel.  Not torch.equal: a
+    # masked key carries weight 2^-126 (not 0) on the polynomial-exp2 lanes, and past the sequence end the paged
+    # path multiplies that with whatever the page holds where the contiguous path sees TMA zero fill (~1e-38).
+    for b, L in enumerate(lens):
+        kg = orc.gather_paged(kp, table[b].tolist(), L, 1).unsqueeze(0).transpose(1, 2).cuda()
+        vg = orc.gather_paged(vp, table[b].tolist(), L, 1).unsqueeze(0).transpose(1, 2).cuda()
+        o2 = pli.flash_attention_forward(q[b:b + 1].cuda(), kg, vg, causal=True)
+        assert (o2.float() - o[b:b + 1].float()).abs().max().item() <= 1e-30, b
+
+
+def test_chunked_prefill_through_paged_cache():
+    """ch08-style chunked prefill: a prompt fed in chunks through PagedKVCache.append + prefill_with_paged gives the
+    same rows as one causal pass over the whole prompt."""
+    torch.manual_seed(5)
+    B, Hq, Hkv, D, N, chunk = 2, 8, 2, 128, 640, 256
+    dev = torch.device("cuda")
+    q = torch.randn(B, Hq, N, D, device=dev, dtype=torch.bfloat16)
+    k = torch.randn(B, N, Hkv, D, device=dev, dtype=torch.bfloat16)
+    v = torch.randn(B, N, Hkv, D, device=dev, dtype=torch.bfloat16)
+    full = pli.flash_attention_forward(q, k.transpose(1, 2), v.transpose(1, 2), causal=True)
+    cache = pli.PagedKVCache(num_blocks=128, block_size=16, num_layers=1, num_heads=Hkv, head_dim=D,
+                             dtype=torch.bfloat16, device="cuda")
+    rids = [7, 9]
+    for a in range(0, N, chunk):
+        e = min(a + chunk, N)
+        cache.append(rids, k[:, a:e], v[:, a:e])
+        o = pli.prefill_with_paged(q[:, :, a:e], cache, rids)
+        assert (o.float() - full[:, :, a:e].float()).abs().max().item() <= 2e-2
