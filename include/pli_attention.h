@@ -101,6 +101,20 @@ int pli_prefill_paged_fwd(const void* q, const void* k_pool, const void* v_pool,
                           const int64_t q_strides[3], const int64_t kv_strides[4], const int64_t o_strides[3],
                           float scale, int dtype, void* stream);
 
+/* The same over RAGGED query lengths: one launch serves a batch whose sequences bring different numbers of new
+ * tokens, the attention step of the mixed prefill/decode batches `MixedBatchScheduler.schedule`
+ * (ch08/mixed_batch.py:63-104) and `ChunkedPrefillScheduler` (ch08/chunked_prefill.py:79-113) emit.
+ *   q, o (total_q, Hq, D) packed over sequences, strides {token, head}; rows [cu_seqlens_q[b], cu_seqlens_q[b+1])
+ *   are the newest tokens of sequence b (cu_seqlens_q: (B+1,) int32 device, non-decreasing, [0] = 0, [B] = total_q);
+ *   query i of sequence b sees key j iff j <= i + (seq_lens[b] - q_len[b]);  seq_lens[b] >= max(q_len[b], 1);
+ *   max_q_len: host upper bound of the q_len[b];  lse (Hq, total_q) or NULL.  Other arguments as above. */
+int pli_prefill_varlen_paged_fwd(const void* q, const void* k_pool, const void* v_pool,
+                                 const int32_t* block_table, const int32_t* seq_lens, const int32_t* cu_seqlens_q,
+                                 void* o, float* lse, int B, int Hq, int Hkv, int64_t total_q, int max_q_len, int D,
+                                 int max_seq_len, int block_size, int table_stride, int layer, int64_t num_pages,
+                                 const int64_t q_strides[2], const int64_t kv_strides[4], const int64_t o_strides[2],
+                                 float scale, int dtype, void* stream);
+
 /* Which kernel pli_prefill_fwd would use for this problem (PLI_KIND_*), without launching. */
 int pli_prefill_kernel_kind(int D, int dtype, const int64_t q_strides[3], const int64_t k_strides[3],
                             const int64_t v_strides[3], const int64_t o_strides[3],

@@ -12,9 +12,10 @@ fails loudly if the library has not been built.
 """
 from ._lib import LIB_PATH, PliError, launch_count, reset_launch_count
 from .decode import (decode_kernel_kind, decode_num_splits, decode_with_cache, decode_with_paged, decode_workspace,
-                     flash_decode, paged_gather, prefill_with_paged)
+                     flash_decode, mixed_batch_attention, paged_gather, prefill_with_paged)
 from .flash_attention import (FlashAttentionConfig, attention_flops, flash_attention, flash_attention_forward,
-                              flash_attention_memory_bytes, flash_attention_paged, prefill_algorithmic_flops,
+                              flash_attention_memory_bytes, flash_attention_paged, flash_attention_varlen_paged,
+                              prefill_algorithmic_flops,
                               prefill_kernel_kind)
 from .kv_cache import KVCache, LayerKVCache, create_caches, kv_append
 from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention
@@ -22,10 +23,11 @@ from .paged_memory import BlockTable, PagedKVCache
 from .sharding import HeadShard, gather_heads, init_distributed, make_shard, shard_kv_heads
 
 __all__ = [
-    "flash_attention_forward", "flash_attention", "flash_attention_paged", "FlashAttentionConfig", "attention_flops",
+    "flash_attention_forward", "flash_attention", "flash_attention_paged", "flash_attention_varlen_paged",
+    "FlashAttentionConfig", "attention_flops",
     "flash_attention_memory_bytes", "prefill_algorithmic_flops", "prefill_kernel_kind",
     "flash_decode", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
-    "decode_kernel_kind", "paged_gather", "prefill_with_paged",
+    "decode_kernel_kind", "paged_gather", "prefill_with_paged", "mixed_batch_attention",
     "KVCache", "LayerKVCache", "create_caches", "kv_append", "BlockTable", "PagedKVCache",
     "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner",
     "HeadShard", "make_shard", "shard_kv_heads", "gather_heads", "init_distributed",

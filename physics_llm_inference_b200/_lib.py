@@ -32,6 +32,9 @@ _SIGNATURES = {
     "pli_prefill_paged_fwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_float,
                                         C.c_int, _VP]),
+    "pli_prefill_varlen_paged_fwd": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _I64P,
+                                               _I64P, _I64P, C.c_float, C.c_int, _VP]),
     "pli_prefill_kernel_kind": (C.c_int, [C.c_int, C.c_int, _I64P, _I64P, _I64P, _I64P, _VP, _VP, _VP, _VP]),
     "pli_decode_num_splits": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "pli_decode_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -53,10 +53,10 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
                            const int64_t* vs, const int64_t* os, float scale, int causal, int dtype,
                            cudaStream_t stream);
 int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table,
-                                 const int32_t* seq_lens, void* o, float* lse, int B, int Hq, int Hkv, int Nq, int D,
-                                 int max_seq_len, int block_size, int table_stride, int layer, int64_t num_pages,
-                                 const int64_t* qs, const int64_t* kvs, const int64_t* os, float scale, int dtype,
-                                 cudaStream_t stream);
+                                 const int32_t* seq_lens, const int32_t* cu_seqlens_q, int64_t total_q, void* o, float* lse,
+                                 int B, int Hq, int Hkv, int Nq, int D, int max_seq_len, int block_size, int table_stride,
+                                 int layer, int64_t num_pages, const int64_t* qs, const int64_t* kvs, const int64_t* os,
+                                 float scale, int dtype, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------

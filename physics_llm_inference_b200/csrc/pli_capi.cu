@@ -170,7 +170,44 @@ extern "C" int pli_prefill_paged_fwd(const void* q, const void* k_pool, const vo
             return set_error(PLI_ERR_INVALID, "q/o strides must be non-negative multiples of 8 elements");
     for (int i = 0; i < 4; ++i)
         if (kv_strides[i] % 8 || kv_strides[i] < 0) return set_error(PLI_ERR_INVALID, "pool strides must be multiples of 8 elements");
-    return launch_prefill_tcgen05_paged(q, k_pool, v_pool, block_table, seq_lens, o, lse, B, Hq, Hkv, Nq, D, max_seq_len,
-                                        block_size, table_stride, layer, num_pages, q_strides, kv_strides, o_strides, scale,
-                                        dtype, stream);
+    return launch_prefill_tcgen05_paged(q, k_pool, v_pool, block_table, seq_lens, nullptr, 0, o, lse, B, Hq, Hkv, Nq, D,
+                                        max_seq_len, block_size, table_stride, layer, num_pages, q_strides, kv_strides,
+                                        o_strides, scale, dtype, stream);
+}
+
+extern "C" int pli_prefill_varlen_paged_fwd(const void* q, const void* k_pool, const void* v_pool,
+                                            const int32_t* block_table, const int32_t* seq_lens,
+                                            const int32_t* cu_seqlens_q, void* o, float* lse, int B, int Hq, int Hkv,
+                                            int64_t total_q, int max_q_len, int D, int max_seq_len, int block_size,
+                                            int table_stride, int layer, int64_t num_pages, const int64_t q_strides[2],
+                                            const int64_t kv_strides[4], const int64_t o_strides[2], float scale,
+                                            int dtype, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!q || !k_pool || !v_pool || !block_table || !seq_lens || !cu_seqlens_q || !o)
+        return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (!q_strides || !kv_strides || !o_strides) return set_error(PLI_ERR_INVALID, "null stride array");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || total_q <= 0 || max_q_len <= 0 || D <= 0 || max_seq_len <= 0 || num_pages <= 0)
+        return set_error(PLI_ERR_INVALID, "non-positive dimension");
+    if (total_q > 0x7fffffff) return set_error(PLI_ERR_UNSUPPORTED, "total_q exceeds 2^31-1");
+    if (Hq % Hkv != 0) return set_error(PLI_ERR_INVALID, "Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
+    if (layer < 0) return set_error(PLI_ERR_INVALID, "negative layer");
+    if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "current CUDA device is not sm_100 (B200)");
+    if (dtype != PLI_BF16 && dtype != PLI_F16) return set_error(PLI_ERR_UNSUPPORTED, "varlen paged prefill takes bf16/f16");
+    if (D != 64 && D != 128) return set_error(PLI_ERR_UNSUPPORTED, "varlen paged prefill supports head_dim 64 and 128, got %d", D);
+    if (block_size != 16 && block_size != 32 && block_size != 64 && block_size != 128)
+        return set_error(PLI_ERR_UNSUPPORTED, "varlen paged prefill supports page sizes 16, 32, 64, 128, got %d", block_size);
+    if (!(scale > 0.f)) return set_error(PLI_ERR_UNSUPPORTED, "varlen paged prefill needs scale > 0");
+    const uintptr_t ptrs = reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k_pool) |
+                           reinterpret_cast<uintptr_t>(v_pool) | reinterpret_cast<uintptr_t>(o);
+    if (ptrs & 15) return set_error(PLI_ERR_INVALID, "q, o and the pools must be 16-byte aligned");
+    for (int i = 0; i < 2; ++i)
+        if (q_strides[i] % 8 || o_strides[i] % 8 || q_strides[i] <= 0 || o_strides[i] <= 0)
+            return set_error(PLI_ERR_INVALID, "q/o strides must be positive multiples of 8 elements");
+    for (int i = 0; i < 4; ++i)
+        if (kv_strides[i] % 8 || kv_strides[i] < 0) return set_error(PLI_ERR_INVALID, "pool strides must be multiples of 8 elements");
+    // the launcher takes {batch, head, token}: the packed tensors have no batch dimension
+    const int64_t qs[3] = {0, q_strides[1], q_strides[0]}, os[3] = {0, o_strides[1], o_strides[0]};
+    return launch_prefill_tcgen05_paged(q, k_pool, v_pool, block_table, seq_lens, cu_seqlens_q, total_q, o, lse, B, Hq, Hkv,
+                                        max_q_len, D, max_seq_len, block_size, table_stride, layer, num_pages, qs, kv_strides,
+                                        os, scale, dtype, stream);
 }

@@ -80,6 +80,12 @@ struct PrefillParams {
     const int32_t* table;
     const int32_t* seq_lens;
     int table_stride, page_size, layer, box_rows;
+    // ragged query lengths (paged kernels only): q / o are packed (total_q, Hq, D), rows [cu_q[b], cu_q[b+1]) belong
+    // to sequence b; Nq is then the host's upper bound of the per-sequence lengths (it sizes the schedule)
+    const int32_t* cu_q;
+    uint8_t* o_base;                  // raw o pointer + element strides for the predicated store of ragged tiles
+    int64_t o_st_tok, o_st_head;
+    int64_t lse_sb, lse_sh;           // lse index = b * lse_sb + h * lse_sh + (row inside the q tensor)
 };
 
 // CTA 0 timeline: each tracing warp owns region `region` of the buffer and keeps its own cursor in a
@@ -98,10 +104,12 @@ __device__ __forceinline__ void trace_event(const PrefillParams& p, int lane, in
 
 constexpr int kHN = 64;                // keys per softmax / MMA half-step (half of a KV tile)
 
-__device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& p, int nk) {
-    // number of 64-key half-steps a Q tile starting at row q0_tile attends to (>= 1)
+__device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& p, int nk, int nq) {
+    // number of 64-key half-steps a Q tile starting at row q0_tile attends to (>= 1; a tile past the last query
+    // row still runs one half-step so that every role sees the same barrier phases, and stores nothing)
     int kmax = nk;
-    if (p.causal) kmax = min(nk, q0_tile + kBM + (nk - p.Nq));
+    if (p.causal) kmax = min(nk, q0_tile + kBM + (nk - nq));
+    if (q0_tile >= nq) kmax = 1;
     kmax = max(kmax, 1);
     return (kmax + kHN - 1) / kHN;
 }
@@ -112,6 +120,8 @@ struct WorkItem {
     int n[2];             // 64-key half-steps per Q tile (n[1] >= n[0])
     int n_kv;             // 128-key K/V tiles to load
     int nk;               // keys of this item's sequence (p.Nk, or seq_lens[b] with paged K/V)
+    int nq;               // query rows of this item's sequence (p.Nq, or cu_q[b+1] - cu_q[b])
+    int qbase, bq;        // TMA coordinates of the sequence's first q row: (token qbase, batch bq)
 };
 
 // Static persistent schedule, longest item first.  Round i hands items [i*G, (i+1)*G) to the G CTAs, in
@@ -154,8 +164,16 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
         it.q0[1] = it.q0[0] + kBM;
     }
     it.nk = p.seq_lens != nullptr ? p.seq_lens[it.b] : p.Nk;
-    it.n[0] = half_steps_for(it.q0[0], p, it.nk);
-    it.n[1] = half_steps_for(it.q0[1], p, it.nk);
+    it.nq = p.Nq;
+    it.qbase = 0;
+    it.bq = it.b;
+    if (p.cu_q != nullptr) {
+        it.qbase = p.cu_q[it.b];
+        it.nq = p.cu_q[it.b + 1] - it.qbase;
+        it.bq = 0;
+    }
+    it.n[0] = half_steps_for(it.q0[0], p, it.nk, it.nq);
+    it.n[1] = half_steps_for(it.q0[1], p, it.nk, it.nq);
     if (it.n[1] < it.n[0]) it.n[1] = it.n[0];
     it.n_kv = (it.n[1] + 1) >> 1;
     return it;
@@ -261,7 +279,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const WorkItem it = decode_item(w, p);
             const int q_tile0 = it.q0[t];
             const int q_row = q_tile0 + row;
-            const int nk = it.nk, off = it.nk - p.Nq;
+            const int nk = it.nk, off = it.nk - it.nq;
             const int nt = it.n[t];
             float m_ref = -INFINITY;                      // reference max (raw score units)
             float d = 0.f;                                // running row sum relative to m_ref
@@ -406,11 +424,17 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 if (lane == 0) mbar_arrive(&stats_free[t]);
                 const float inv = 1.f / dsum;
                 const int q_tile0 = it.q0[t];
+                // ragged tile of a packed q tensor: a TMA box would spill into the next sequence's rows, so the rows
+                // go from registers to global memory under a predicate (uniform over the 128 epilogue threads)
+                bool direct = false;
+                if constexpr (kPaged) direct = p.cu_q != nullptr && q_tile0 + kBM > it.nq;
 #pragma unroll
                 for (int hf = 0; hf < kHalves; ++hf) {
                     // the previous TMA store must have finished reading sO before it is overwritten
-                    if (warp == 8 && lane == 0) tma_store_wait_read<0>();
-                    named_bar_sync(kBarEpilogue, 128);
+                    if (!direct) {
+                        if (warp == 8 && lane == 0) tma_store_wait_read<0>();
+                        named_bar_sync(kBarEpilogue, 128);
+                    }
 #pragma unroll
                     for (int c2 = 0; c2 < 2; ++c2) {
                         const int ch = hf * 2 + c2;                   // 32-column chunk of O_t
@@ -424,6 +448,12 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             if (lane == 0) mbar_arrive(&pv_ok[t * 2]);
                         }
                         uint8_t* srow = sO + row * 128;
+                        uint8_t* grow = nullptr;
+                        if constexpr (kPaged) {
+                            if (direct && q_tile0 + row < it.nq)
+                                grow = p.o_base + ((int64_t)(it.qbase + q_tile0 + row) * p.o_st_tok +
+                                                   (int64_t)it.h[t] * p.o_st_head + ch * 32) * 2;
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             uint4 val;
@@ -432,18 +462,21 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             val.z = pack2<kBf16>(orr[8 * i + 4] * inv, orr[8 * i + 5] * inv);
                             val.w = pack2<kBf16>(orr[8 * i + 6] * inv, orr[8 * i + 7] * inv);
                             const int chunk = c2 * 4 + i;             // 16-byte chunk inside the 128-byte row
-                            *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = val;
+                            if (!direct) *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = val;
+                            else if (grow != nullptr) reinterpret_cast<uint4*>(grow)[i] = val;
                         }
                     }
-                    fence_proxy_async();
-                    named_bar_sync(kBarEpilogue, 128);
-                    if (warp == 8 && lane == 0 && q_tile0 < p.Nq) {
-                        tma_store_4d(&map_o, sO, hf * 64, q_tile0, it.h[t], it.b);
-                        tma_store_commit();
+                    if (!direct) {
+                        fence_proxy_async();
+                        named_bar_sync(kBarEpilogue, 128);
+                        if (warp == 8 && lane == 0 && q_tile0 < it.nq) {
+                            tma_store_4d(&map_o, sO, hf * 64, it.qbase + q_tile0, it.h[t], it.bq);
+                            tma_store_commit();
+                        }
                     }
                 }
-                if (p.lse != nullptr && q_tile0 + row < p.Nq)
-                    p.lse[((int64_t)it.b * p.Hq + it.h[t]) * p.Nq + q_tile0 + row] = (mlog2 + log2f(dsum)) * kLn2;
+                if (p.lse != nullptr && q_tile0 + row < it.nq)
+                    p.lse[it.b * p.lse_sb + it.h[t] * p.lse_sh + it.qbase + q_tile0 + row] = (mlog2 + log2f(dsum)) * kLn2;
                 // s_full[t*2+h] completed ceil((n_t - h) / 2) phases in this item
                 sf_base ^= (uint32_t)(((it.n[t] + 1) >> 1) & 1) << (t * 2);
                 sf_base ^= (uint32_t)((it.n[t] >> 1) & 1) << (t * 2 + 1);
@@ -572,7 +605,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
                         for (int hf = 0; hf < kHalves; ++hf)
                             tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
-                                        it.q0[t], it.h[t], it.b);
+                                        it.qbase + it.q0[t], it.h[t], it.bq);
                     }
                 };
                 // paged: this lane's box of every K/V tile covers tile rows [row0, row0 + box_rows); its page id is
@@ -583,7 +616,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const int row0 = rank * rows_cta + lane * p.box_rows;
                 auto page_of = [&](int j) -> int {
                     if (!kPaged || lane >= n_boxes) return 0;
-                    const int key = min(j * kBN + row0, it.nk - 1);
+                    const int key = max(min(j * kBN + row0, it.nk - 1), 0);
                     return p.table[(int64_t)it.b * p.table_stride + key / p.page_size];
                 };
                 auto load_kv = [&](const CUtensorMap* map, int j, int page) {
@@ -593,7 +626,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     if constexpr (kPaged) {
                         __syncwarp();
                         if (lane < n_boxes) {
-                            const int in_page = min(j * kBN + row0, it.nk - 1) % p.page_size;
+                            const int in_page = max(min(j * kBN + row0, it.nk - 1), 0) % p.page_size;
                             const int slot0 = in_page - in_page % p.box_rows;      // box-aligned slot inside the page
 #pragma unroll
                             for (int hf = 0; hf < kHalves; ++hf) {
@@ -826,24 +859,32 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
     p.table = nullptr;
     p.seq_lens = nullptr;
     p.table_stride = p.page_size = p.layer = p.box_rows = 0;
+    p.cu_q = nullptr;
+    p.o_base = nullptr;
+    p.o_st_tok = p.o_st_head = 0;
+    p.lse_sb = (int64_t)Hq * Nq;
+    p.lse_sh = Nq;
 }
 
 }  // namespace
 
+// cu_seqlens_q == nullptr: q / o are (B, Hq, Nq, D) with strides {batch, head, token}.  Otherwise they are packed
+// (total_q, Hq, D) with strides {unused, head, token}, Nq is the upper bound of the per-sequence query lengths.
 int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table,
-                                 const int32_t* seq_lens, void* o, float* lse, int B, int Hq, int Hkv, int Nq, int D,
-                                 int max_seq_len, int block_size, int table_stride, int layer, int64_t num_pages,
-                                 const int64_t* qs, const int64_t* kvs, const int64_t* os, float scale, int dtype,
-                                 cudaStream_t stream) {
+                                 const int32_t* seq_lens, const int32_t* cu_seqlens_q, int64_t total_q, void* o, float* lse,
+                                 int B, int Hq, int Hkv, int Nq, int D, int max_seq_len, int block_size, int table_stride,
+                                 int layer, int64_t num_pages, const int64_t* qs, const int64_t* kvs, const int64_t* os,
+                                 float scale, int dtype, cudaStream_t stream) {
     const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
     const int rows_cta = pairs ? kHN : kBN;
     const int box_rows = block_size < rows_cta ? block_size : rows_cta;
     CUtensorMap mq, mk, mv, mo;
     int rc;
-    if ((rc = make_map_4d(&mq, q, dtype, D, Nq, Hq, B, qs))) return rc;
+    const bool packed = cu_seqlens_q != nullptr;
+    if ((rc = make_map_4d(&mq, q, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, qs))) return rc;
     if ((rc = make_pool_map(&mk, k_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
     if ((rc = make_pool_map(&mv, v_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
-    if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
+    if ((rc = make_map_4d(&mo, o, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, os))) return rc;
     PrefillParams p;
     p.lse = lse;
     p.B = B;
@@ -862,6 +903,14 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
     p.page_size = block_size;
     p.layer = layer;
     p.box_rows = box_rows;
+    if (packed) {
+        p.cu_q = cu_seqlens_q;
+        p.o_base = static_cast<uint8_t*>(o);
+        p.o_st_head = os[1];
+        p.o_st_tok = os[2];
+        p.lse_sb = 0;               // lse is (Hq, total_q)
+        p.lse_sh = total_q;
+    }
     const bool bf16 = dtype == PLI_BF16;
 #define PLI_GO(DD, BF)                                                                                  \
     return pairs ? launch_t<DD, BF, 2, true>(mq, mk, mv, mo, p, stream) : launch_t<DD, BF, 1, true>(mq, mk, mv, mo, p, stream)

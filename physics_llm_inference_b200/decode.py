@@ -191,6 +191,40 @@ def prefill_with_paged(q: torch.Tensor, paged: PagedKVCache, request_ids, *, lay
     return flash_attention_paged(q, paged.k_cache, paged.v_cache, bt, lens, layer=layer, max_seq_len=max_len, **kw)
 
 
+def mixed_batch_attention(q: torch.Tensor, paged: PagedKVCache, prefill_ids, prefill_lens, decode_ids, *,
+                          layer: int = 0, scale: float | None = None) -> torch.Tensor:
+    """Attention of one mixed prefill/decode step (`MixedBatch` of ch08/mixed_batch.py:19-31: `prefill_requests`
+    bringing `prompt_len`/chunk tokens each, `decode_requests` bringing one) over a `PagedKVCache` whose pages
+    already hold this step's K/V.
+
+    q (prefill_tokens + len(decode_ids), Hq, D): the prefill requests' new tokens in request order, then one row per
+    decode request.  Two launches: the ragged prefill kernel for the prefill rows, the split-KV decode kernel
+    (writing straight into the packed output) for the decode rows.  Returns o shaped like q."""
+    from .flash_attention import flash_attention_varlen_paged
+    if paged.k_cache is None:
+        raise RuntimeError("PagedKVCache has no device pools (constructed without CUDA)")
+    prefill_ids, decode_ids = list(prefill_ids), list(decode_ids)
+    prefill_lens = [int(n) for n in prefill_lens]
+    if len(prefill_lens) != len(prefill_ids):
+        raise ValueError("one length per prefill request")
+    tp = sum(prefill_lens)
+    if q.dim() != 3 or q.shape[0] != tp + len(decode_ids):
+        raise RuntimeError(f"q must be ({tp + len(decode_ids)}, Hq, D); got {tuple(q.shape)}")
+    for r, n in zip(prefill_ids, prefill_lens):
+        if not 0 < n <= paged.block_tables[r].num_tokens:
+            raise ValueError(f"request {r}: {n} new tokens but {paged.block_tables[r].num_tokens} cached")
+    out = torch.empty((q.shape[0], q.shape[1], q.shape[2]), dtype=q.dtype, device=q.device)
+    if prefill_ids:
+        bt, lens = paged.block_table_tensor(prefill_ids, device=q.device)
+        cu = torch.tensor([0] + prefill_lens, dtype=torch.int32).cumsum(0, dtype=torch.int32).to(q.device)
+        max_len = max(paged.block_tables[r].num_tokens for r in prefill_ids)
+        out[:tp] = flash_attention_varlen_paged(q[:tp], paged.k_cache, paged.v_cache, bt, lens, cu, max(prefill_lens),
+                                                layer=layer, scale=scale, max_seq_len=max_len)
+    if decode_ids:
+        decode_with_paged(q[tp:], paged, decode_ids, layer=layer, scale=scale, out=out[tp:])
+    return out
+
+
 def paged_gather(store: torch.Tensor, block_tables: torch.Tensor, seq_lens: torch.Tensor, max_len: int,
                  layer: int = 0) -> torch.Tensor:
     """Gather one layer of a paged pool to (B, max_len, Hkv, D) with the kernels' address rule

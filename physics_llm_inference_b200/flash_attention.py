@@ -200,3 +200,56 @@ def flash_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.T
             _lib.i64(*out.stride()[:3]), float(scale), _lib.dtype_code(q.dtype), _lib.current_stream_ptr(q.device))
     _lib.check(rc)
     return (out, lse) if return_lse else out
+
+
+def flash_attention_varlen_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_tables: torch.Tensor,
+                                 seq_lens: torch.Tensor, cu_seqlens_q: torch.Tensor, max_q_len: int, *, layer: int = 0,
+                                 scale: float | None = None, max_seq_len: int | None = None, return_lse: bool = False):
+    """`flash_attention_paged` for ragged query lengths: q (total_q, Hq, D) packs the newest tokens of every sequence,
+    rows [cu_seqlens_q[b], cu_seqlens_q[b+1]) belong to sequence b (cu_seqlens_q (B+1,) int32 CUDA, max_q_len a host
+    bound of the per-sequence lengths).  One launch serves the prefill side of a mixed batch
+    (ch08/mixed_batch.py:63-104).  Returns o (total_q, Hq, D) (and lse (Hq, total_q) float32 when return_lse)."""
+    if not (q.is_cuda and k_pool.is_cuda and v_pool.is_cuda):
+        raise RuntimeError("flash_attention_varlen_paged runs on CUDA tensors only (no CPU fallback)")
+    if q.dim() != 3 or k_pool.dim() != 5:
+        raise RuntimeError(f"q must be (total_q, Hq, D) and the pools (P, layers, bs, Hkv, D); got {tuple(q.shape)}, {tuple(k_pool.shape)}")
+    if not (q.dtype == k_pool.dtype == v_pool.dtype):
+        raise RuntimeError("q and the pools must share a dtype")
+    if k_pool.shape != v_pool.shape or k_pool.stride() != v_pool.stride() or k_pool.stride(-1) != 1:
+        raise RuntimeError("k and v pools must have the same shape/strides and a unit head_dim stride")
+    T, Hq, D = q.shape
+    P, n_layers, bs, Hkv, Dk = k_pool.shape
+    B = seq_lens.shape[0]
+    if Dk != D or Hq % Hkv != 0:
+        raise RuntimeError(f"pools {tuple(k_pool.shape)} do not match q {tuple(q.shape)}")
+    if not 0 <= layer < n_layers:
+        raise IndexError(f"layer {layer} out of range for {n_layers} layers")
+    if block_tables.dtype != torch.int32 or not block_tables.is_cuda or block_tables.dim() != 2 or block_tables.shape[0] != B:
+        raise RuntimeError("block_tables must be a (B, max_pages) CUDA int32 tensor")
+    for name, x, n in (("seq_lens", seq_lens, B), ("cu_seqlens_q", cu_seqlens_q, B + 1)):
+        if x.dtype != torch.int32 or not x.is_cuda or x.shape != (n,):
+            raise RuntimeError(f"{name} must be a ({n},) CUDA int32 tensor")
+    if T == 0:
+        raise RuntimeError("empty q")
+    if not 0 < int(max_q_len) <= T:
+        raise ValueError(f"max_q_len ({max_q_len}) outside (0, total_q={T}]")
+    if block_tables.stride(-1) != 1:
+        block_tables = block_tables.contiguous()
+    seq_lens, cu_seqlens_q = seq_lens.contiguous(), cu_seqlens_q.contiguous()
+    q = _unit_inner(q)
+    cap = block_tables.shape[1] * bs
+    max_seq_len = cap if max_seq_len is None else min(int(max_seq_len), cap)
+    if scale is None:
+        scale = D ** -0.5
+    out = torch.empty((T, Hq, D), dtype=q.dtype, device=q.device)
+    lse = torch.empty((Hq, T), dtype=torch.float32, device=q.device) if return_lse else None
+    lib = _lib.load()
+    with _lib.on_device(q.device):
+        rc = lib.pli_prefill_varlen_paged_fwd(
+            q.data_ptr(), k_pool.data_ptr(), v_pool.data_ptr(), block_tables.data_ptr(), seq_lens.data_ptr(),
+            cu_seqlens_q.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None, B, Hq, Hkv, T,
+            int(max_q_len), D, max_seq_len, bs, block_tables.stride(0), layer, P, _lib.i64(*q.stride()[:2]),
+            _lib.i64(*k_pool.stride()[:4]), _lib.i64(*out.stride()[:2]), float(scale), _lib.dtype_code(q.dtype),
+            _lib.current_stream_ptr(q.device))
+    _lib.check(rc)
+    return (out, lse) if return_lse else out

@@ -222,3 +222,39 @@ def test_shared_prefix_pages_alias():
     # the parent's pages were not disturbed by the child's appends
     got = pli.paged_gather(cache.k_cache, *cache.block_table_tensor([1]), L0)
     assert torch.equal(got[0], k0[0])
+
+
+def test_mixed_prefill_decode_batch():
+    """One step of a ch08 mixed batch: two prompts of different length prefilled while three requests decode."""
+    torch.manual_seed(11)
+    Hq, Hkv, D, bs = 8, 2, 128, 16
+    dev = torch.device("cuda")
+    cache = pli.PagedKVCache(num_blocks=256, block_size=bs, num_layers=1, num_heads=Hkv, head_dim=D,
+                             dtype=torch.bfloat16, device="cuda")
+    history = {}                                    # request id -> (k, v) of everything cached, (n, Hkv, D)
+
+    def feed(rid, n):
+        k = torch.randn(1, n, Hkv, D, device=dev, dtype=torch.bfloat16)
+        v = torch.randn(1, n, Hkv, D, device=dev, dtype=torch.bfloat16)
+        cache.append([rid], k, v)
+        pk, pv = history.get(rid, (k[:, :0], v[:, :0]))
+        history[rid] = (torch.cat([pk, k], 1), torch.cat([pv, v], 1))
+
+    for rid, n in ((3, 500), (4, 77), (5, 1300)):   # decoding requests with some context already cached
+        feed(rid, n)
+    prefill_ids, prefill_lens, decode_ids = [10, 11], [333, 90], [3, 4, 5]
+    for rid, n in zip(prefill_ids, prefill_lens):   # this step's K/V: whole prompts for the new requests ...
+        feed(rid, n)
+    for rid in decode_ids:                          # ... and one token for each decoding request
+        feed(rid, 1)
+    T = sum(prefill_lens) + len(decode_ids)
+    q = torch.randn(T, Hq, D, device=dev, dtype=torch.bfloat16)
+    o = pli.mixed_batch_attention(q, cache, prefill_ids, prefill_lens, decode_ids)
+    assert o.shape == q.shape
+    at = 0
+    for rid, n in list(zip(prefill_ids, prefill_lens)) + [(r, 1) for r in decode_ids]:
+        k, v = history[rid]
+        ro, _ = orc.cached_attention_oracle(q[at:at + n].transpose(0, 1).unsqueeze(0).float().cpu(),
+                                            k.float().cpu(), v.float().cpu(), k.shape[1])
+        assert (o[at:at + n].float().cpu().transpose(0, 1) - ro[0]).abs().max().item() <= 2e-2, rid
+        at += n

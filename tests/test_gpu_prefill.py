@@ -266,3 +266,30 @@ def test_chunked_prefill_through_paged_cache():
         cache.append(rids, k[:, a:e], v[:, a:e])
         o = pli.prefill_with_paged(q[:, :, a:e], cache, rids)
         assert (o.float() - full[:, :, a:e].float()).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("bs,D,Hkv,G,q_lens,lens", [
+    (16, 128, 2, 4, [128, 37, 300, 1], [512, 300, 300, 77]),       # CTA pairs; full, ragged, multi-tile and 1-row chunks
+    (16, 128, 1, 2, [200, 129, 5], [777, 129, 900]),               # head pairs, tiles straddling sequence ends
+    (64, 64, 2, 1, [96, 260, 31], [1000, 260, 640]),               # MHA row-pair items, D 64
+    (32, 128, 1, 3, [64, 257], [64, 300]),                         # odd group (row pairs), whole prompt as the chunk
+])
+def test_varlen_paged_prefill_parity(bs, D, Hkv, G, q_lens, lens):
+    """Ragged query lengths over the paged pools: every sequence matches the oracle run on it alone, and rows of
+    the packed output that belong to no tile of a sequence are never clobbered by a neighbour's store."""
+    dtype = torch.bfloat16
+    B, Hq = len(lens), Hkv * G
+    _, kp, vp, table, lens_t = orc.seeded_paged(71, B, Hq, Hkv, D, bs, lens, num_layers=2, dtype=dtype)
+    g = torch.Generator().manual_seed(72)
+    T = sum(q_lens)
+    q = torch.randn(T, Hq, D, generator=g).to(dtype)
+    cu = torch.tensor([0] + q_lens, dtype=torch.int32).cumsum(0, dtype=torch.int32)
+    o, lse = pli.flash_attention_varlen_paged(q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens_t.cuda(), cu.cuda(),
+                                              max(q_lens), layer=1, return_lse=True, max_seq_len=max(lens))
+    assert o.shape == (T, Hq, D) and lse.shape == (Hq, T)
+    for b in range(B):
+        a, e = int(cu[b]), int(cu[b + 1])
+        qb = q[a:e].transpose(0, 1).unsqueeze(0)                                   # (1, Hq, nq, D)
+        ro, rlse = orc.paged_decode_oracle(qb, kp, vp, table[b:b + 1], lens_t[b:b + 1], layer=1)
+        assert (o[a:e].float().cpu().transpose(0, 1) - ro[0]).abs().max().item() <= 2e-2, b
+        assert (lse[:, a:e].cpu() - rlse[0]).abs().max().item() <= 1e-3, b
