@@ -547,11 +547,11 @@ def main():
     if decode is not None:
         line["decode"] = decode
     if not args.no_cpu_baseline and world == 1:
-        val, dt, threads = cpu_prefill_sample()
+        val, dt, threads = cpu_prefill_sample(reps=4)
         s = CPU_SAMPLE
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"oracle port (ch06 recurrence + ch01 mask/GQA, fp32) on B{s['B']} x {s['Hq']}q/{s['Hkv']}kv "
-                                          f"x N{s['N']} x D{s['D']} of C2 = 1/4 of the step, {dt:.1f} s, 1 pass"}
+                                          f"x N{s['N']} x D{s['D']} of C2 = 1/4 of the step, best of 4 passes ({dt:.1f} s each)"}
         if decode is not None:
             dval, ddt, _ = cpu_decode_sample()
             s = CPU_DECODE_SAMPLE

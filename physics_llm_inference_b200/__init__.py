@@ -18,7 +18,7 @@ from .flash_attention import (FlashAttentionConfig, attention_flops, flash_atten
                               prefill_algorithmic_flops,
                               prefill_kernel_kind)
 from .kv_cache import KVCache, LayerKVCache, create_caches, kv_append
-from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention
+from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention, TensorParallelGQA
 from .paged_memory import BlockTable, PagedKVCache
 from .sharding import HeadShard, gather_heads, init_distributed, make_shard, shard_kv_heads
 
@@ -29,7 +29,7 @@ __all__ = [
     "flash_decode", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
     "decode_kernel_kind", "paged_gather", "prefill_with_paged", "mixed_batch_attention",
     "KVCache", "LayerKVCache", "create_caches", "kv_append", "BlockTable", "PagedKVCache",
-    "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner",
+    "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner", "TensorParallelGQA",
     "HeadShard", "make_shard", "shard_kv_heads", "gather_heads", "init_distributed",
     "PliError", "LIB_PATH", "launch_count", "reset_launch_count",
 ]

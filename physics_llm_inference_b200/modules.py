@@ -145,3 +145,60 @@ class DecodeGraphRunner:
         self.static_v.copy_(v_new.reshape(self.static_v.shape))
         self.graph.replay()
         return self.static_out.clone()
+
+
+class TensorParallelGQA(nn.Module):
+    """`GroupedQueryAttention` sharded over KV-head groups: q/k/v projections are
+    column-parallel (`ColumnParallelLinear`, ch09/tensor_parallel.py:15-40: this rank's heads only), the
+    attention kernels run on the local heads with no exchange, and the output projection is row-parallel
+    (`RowParallelLinear`, ch09/tensor_parallel.py:43-68) followed by the all-reduce the reference only
+    describes (ch09/nccl_primitives.py:45-67 models its cost).  `world_size` must divide num_kv_heads."""
+
+    def __init__(self, hidden_dim: int, num_heads: int, num_kv_heads: int, world_size: int = 1, rank: int = 0,
+                 process_group=None):
+        super().__init__()
+        assert num_heads % num_kv_heads == 0
+        if num_kv_heads % world_size != 0:
+            raise ValueError(f"world_size ({world_size}) must divide num_kv_heads ({num_kv_heads})")
+        if not 0 <= rank < world_size:
+            raise ValueError(f"rank {rank} outside [0, {world_size})")
+        self.world_size, self.rank, self.process_group = world_size, rank, process_group
+        self.hidden_dim = hidden_dim
+        self.head_dim = hidden_dim // num_heads
+        self.num_heads = num_heads // world_size              # local q heads
+        self.num_kv_heads = num_kv_heads // world_size        # local kv heads
+        self.q_proj = nn.Linear(hidden_dim, self.num_heads * self.head_dim, bias=False)
+        self.k_proj = nn.Linear(hidden_dim, self.num_kv_heads * self.head_dim, bias=False)
+        self.v_proj = nn.Linear(hidden_dim, self.num_kv_heads * self.head_dim, bias=False)
+        self.o_proj = nn.Linear(self.num_heads * self.head_dim, hidden_dim, bias=False)
+
+    @classmethod
+    def from_full(cls, full: GroupedQueryAttention, world_size: int, rank: int, process_group=None):
+        """This rank's shard of an unsharded block: rows of q/k/v weights, columns of the o weight."""
+        tp = cls(full.hidden_dim, full.num_heads, full.num_kv_heads, world_size, rank, process_group)
+        tp = tp.to(device=full.q_proj.weight.device, dtype=full.q_proj.weight.dtype)
+        nq, nkv = tp.num_heads * tp.head_dim, tp.num_kv_heads * tp.head_dim
+        with torch.no_grad():
+            tp.q_proj.weight.copy_(full.q_proj.weight[rank * nq:(rank + 1) * nq])
+            tp.k_proj.weight.copy_(full.k_proj.weight[rank * nkv:(rank + 1) * nkv])
+            tp.v_proj.weight.copy_(full.v_proj.weight[rank * nkv:(rank + 1) * nkv])
+            tp.o_proj.weight.copy_(full.o_proj.weight[:, rank * nq:(rank + 1) * nq])
+        return tp
+
+    def partial_forward(self, x: torch.Tensor, causal: bool = True) -> torch.Tensor:
+        """This rank's summand of the block output (before the all-reduce)."""
+        batch, seq_len, _ = x.shape
+        q = self.q_proj(x).view(batch, seq_len, self.num_heads, self.head_dim).transpose(1, 2)
+        k = self.k_proj(x).view(batch, seq_len, self.num_kv_heads, self.head_dim).transpose(1, 2)
+        v = self.v_proj(x).view(batch, seq_len, self.num_kv_heads, self.head_dim).transpose(1, 2)
+        attn = flash_attention_forward(q, k, v, causal=causal)
+        return self.o_proj(attn.transpose(1, 2).reshape(batch, seq_len, self.num_heads * self.head_dim))
+
+    def reduce(self, partial: torch.Tensor) -> torch.Tensor:
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.process_group)
+        return partial
+
+    def forward(self, x: torch.Tensor, causal: bool = True) -> torch.Tensor:
+        return self.reduce(self.partial_forward(x, causal))

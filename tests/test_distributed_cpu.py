@@ -42,3 +42,30 @@ def test_gloo_world2_shard_and_gather(tmp_path, Hq, Hkv, B):
     mp.spawn(_worker, args=(2, port, Hq, Hkv, B, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert int(torch.load(os.path.join(tmp_path, f"ok{r}.pt"))) == 1
+
+
+def _tp_worker(rank, world, port, out_dir):
+    import physics_llm_inference_b200 as pli
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    pli.init_distributed("gloo")
+    torch.manual_seed(0)
+    full = pli.GroupedQueryAttention(64, 4, 2)
+    tp = pli.TensorParallelGQA.from_full(full, world, rank)
+    # host logic only (no attention call on CPU): the shard holds this rank's rows / columns, and reduce() sums
+    nq = tp.num_heads * tp.head_dim
+    ok = torch.equal(tp.q_proj.weight, full.q_proj.weight[rank * nq:(rank + 1) * nq])
+    ok = ok and torch.equal(tp.o_proj.weight, full.o_proj.weight[:, rank * nq:(rank + 1) * nq])
+    ok = ok and (tp.num_heads, tp.num_kv_heads) == (2, 1)
+    part = torch.full((2, 3), float(rank + 1))
+    ok = ok and torch.equal(tp.reduce(part), torch.full((2, 3), float(sum(range(1, world + 1)))))
+    torch.save(torch.tensor(int(ok)), os.path.join(out_dir, f"tp{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_tensor_parallel_gqa_plumbing(tmp_path):
+    port = _free_port()
+    mp.spawn(_tp_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert int(torch.load(os.path.join(tmp_path, f"tp{r}.pt"))) == 1

@@ -92,3 +92,22 @@ def test_decode_step_under_cuda_graph(paged):
         ref, _ = orc.cached_attention_oracle(q, k_hist, v_hist, L)
         assert (out.float().cpu() - ref[:, :, 0]).abs().max().item() <= 2e-2, i
     assert int(runner.seq_lens[0]) == L0 + steps
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_tensor_parallel_gqa_shards_sum_to_the_full_block(world):
+    """KV-head-sharded GQA block: the ranks' partial outputs (what the all-reduce adds up) sum to the unsharded
+    block's output; bf16 weights, random init."""
+    torch.manual_seed(3)
+    Hq, Hkv, D, B, N = 16, 4, 128, 2, 300
+    full = pli.GroupedQueryAttention(Hq * D, Hq, Hkv).cuda().to(torch.bfloat16)
+    x = torch.randn(B, N, Hq * D, device="cuda", dtype=torch.bfloat16) * 0.5
+    with torch.no_grad():
+        ref = full(x, causal=True).float()
+        parts = [pli.TensorParallelGQA.from_full(full, world, r).partial_forward(x).float() for r in range(world)]
+        one = pli.TensorParallelGQA.from_full(full, 1, 0)(x).float()
+    assert torch.equal(one, ref)
+    tol = 2e-2 * max(1.0, ref.abs().max().item())
+    assert (sum(parts) - ref).abs().max().item() <= tol
+    with pytest.raises(ValueError):
+        pli.TensorParallelGQA(Hq * D, Hq, Hkv, world_size=3, rank=0)
