@@ -20,7 +20,7 @@ from .flash_attention import (FlashAttentionConfig, attention_flops, flash_atten
 from .kv_cache import KVCache, LayerKVCache, create_caches, kv_append
 from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention, TensorParallelGQA
 from .paged_memory import BlockTable, PagedKVCache
-from .sharding import HeadShard, gather_heads, init_distributed, make_shard, shard_kv_heads
+from .sharding import HeadShard, PeerOutput, gather_heads, init_distributed, make_shard, shard_kv_heads
 
 __all__ = [
     "flash_attention_forward", "flash_attention", "flash_attention_paged", "flash_attention_varlen_paged",
@@ -30,6 +30,6 @@ __all__ = [
     "decode_kernel_kind", "paged_gather", "prefill_with_paged", "mixed_batch_attention",
     "KVCache", "LayerKVCache", "create_caches", "kv_append", "BlockTable", "PagedKVCache",
     "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner", "TensorParallelGQA",
-    "HeadShard", "make_shard", "shard_kv_heads", "gather_heads", "init_distributed",
+    "HeadShard", "PeerOutput", "make_shard", "shard_kv_heads", "gather_heads", "init_distributed",
     "PliError", "LIB_PATH", "launch_count", "reset_launch_count",
 ]

@@ -149,6 +149,38 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 // byte offset of (row, 16-byte chunk) inside a [rows][64 el] 128B-swizzled sub-tile
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
+// Fused all-gather of the decode output over NVLink peer memory (pli_decode_fwd_scatter): every rank holds the
+// FULL (B, Hq_total, D) output in peer-mapped memory; a rank's kernel stores its slice into all of them, and the
+// last CTA to finish publishes `epoch` in every rank's flag word for this rank (release at system scope).
+struct PeerScatter {
+    void* o[PLI_MAX_PEERS];
+    uint32_t* flags[PLI_MAX_PEERS];
+    unsigned int* counter;            // local CTA-completion counter (zero between launches)
+    uint32_t epoch;
+    int n, rank;
+    int64_t slice_offset;             // element offset of this rank's (batch, head) slice inside the full tensor
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by one thread of a CTA after the CTA's peer stores were fenced (__threadfence_system) and the CTA
+// synchronised: the last CTA of the grid publishes the epoch to every rank.
+__device__ __forceinline__ void peer_publish(const PeerScatter& ps, unsigned int total_ctas) {
+    const unsigned int prev = atomicAdd(ps.counter, 1u);
+    if (prev == total_ctas - 1) {
+        __threadfence_system();
+        for (int r = 0; r < ps.n; ++r) st_release_sys(ps.flags[r] + ps.rank, ps.epoch);
+        *ps.counter = 0u;             // the next launch on this stream starts from zero
+    }
+}
+
 struct DecodeTmaParams {
     const void* q;
     const int32_t* table;
@@ -161,6 +193,7 @@ struct DecodeTmaParams {
     int64_t qsb, qsh;
     int Hq, Hkv, G, bs, table_stride, layer, S, box_tokens;
     float scale_log2;
+    PeerScatter peer;     // peer.n > 0 (direct output only): o_direct is unused, the slice goes to every rank
 };
 
 template <int kD, bool kBf16, bool kRows16>
@@ -396,7 +429,12 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             }
             const float o_val = den > 0.f ? o / den : 0.f;
             const float lse_val = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
-            if (p.o_direct != nullptr) {
+            if (p.peer.n > 0) {
+                const int64_t off = p.peer.slice_offset + b * p.osb + (h_base + row) * p.osh + d;
+                const elem_t val = from_f32<elem_t>(o_val);
+                for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[off] = val;
+                if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val;
+            } else if (p.o_direct != nullptr) {
                 // single split: this CTA owns the whole sequence, so the combine pass is skipped
                 reinterpret_cast<elem_t*>(p.o_direct)[b * p.osb + (h_base + row) * p.osh + d] = from_f32<elem_t>(o_val);
                 if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val;
@@ -405,6 +443,11 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 p.o_part[prow * kD + d] = o_val;
                 if (d == 0) p.lse_part[prow] = lse_val;
             }
+        }
+        if (p.peer.n > 0) {
+            __threadfence_system();
+            named_bar_sync(1, kConsumerWarps * 32);
+            if (threadIdx.x == 0) peer_publish(p.peer, gridDim.x * gridDim.y * gridDim.z);
         }
     }
 }
@@ -416,7 +459,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __restrict__ o_part,
                                                              const float* __restrict__ lse_part, T* __restrict__ o,
                                                              float* __restrict__ lse, int Hq, int D, int S,
-                                                             int64_t osb, int64_t osh) {
+                                                             int64_t osb, int64_t osh, const PeerScatter peer) {
     const int h = blockIdx.x, b = blockIdx.y;
     const int64_t row = ((int64_t)b * Hq + h) * S;
     float M = -INFINITY;
@@ -434,9 +477,32 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __rest
             const float w = (l == -INFINITY) ? 0.f : __expf(l - M);
             acc = fmaf(w, o_part[(row + s) * D + d], acc);
         }
-        o[b * osb + h * osh + d] = from_f32<T>(acc * inv);
+        const T val = from_f32<T>(acc * inv);
+        if (peer.n > 0) {
+            const int64_t off = peer.slice_offset + b * osb + h * osh + d;
+            for (int r = 0; r < peer.n; ++r) reinterpret_cast<T*>(peer.o[r])[off] = val;
+        } else {
+            o[b * osb + h * osh + d] = val;
+        }
     }
     if (lse != nullptr && threadIdx.x == 0) lse[(int64_t)b * Hq + h] = den > 0.f ? M + logf(den) : -INFINITY;
+    if (peer.n > 0) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) peer_publish(peer, gridDim.x * gridDim.y);
+    }
+}
+
+// One thread per rank spins (acquire, system scope) until that rank's slice of `epoch` has landed here.  The
+// producers never wait on anybody, so this cannot deadlock; a lost peer traps after ~4 s instead of hanging.
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t epoch) {
+    const int r = threadIdx.x;
+    if (r >= n) return;
+    for (long long spin = 0;; ++spin) {
+        if ((int32_t)(ld_acquire_sys(flags + r) - epoch) >= 0) return;
+        __nanosleep(64);
+        if (spin > (1ll << 25)) __trap();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -584,7 +650,7 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
                         int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
                         const int64_t kv_strides[4], float scale, int dtype, int num_splits, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream, void* o_direct, float* lse_direct,
-                        const int64_t* o_strides, bool* wrote_direct) {
+                        const int64_t* o_strides, bool* wrote_direct, const PeerScatter* peer = nullptr) {
     const bool paged = block_table != nullptr;
     if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
     int rc = check_decode_args(q, k_store, v_store, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, paged, num_splits);
@@ -630,6 +696,8 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
         p.S = num_splits;
         p.box_tokens = box_tokens;
         p.scale_log2 = scale * kLog2e;
+        p.peer = PeerScatter{};
+        if (direct && peer != nullptr) p.peer = *peer;
         const int hchunks = (G + 15) / 16;
         dim3 grid(num_splits, Hkv * hchunks, B);
         const bool rows16 = G > 8;
@@ -682,10 +750,10 @@ extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void
                         static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr);
 }
 
-extern "C" int pli_decode_combine(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
-                                  const int64_t o_strides[2], int dtype, void* stream_) {
+static int combine_impl(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
+                        const int64_t o_strides[2], int dtype, void* stream_, const PeerScatter& peer) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (!workspace || !o) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (!workspace || (!o && peer.n == 0)) return set_error(PLI_ERR_INVALID, "null pointer argument");
     if (B <= 0 || Hq <= 0 || D <= 0 || num_splits <= 0) return set_error(PLI_ERR_INVALID, "non-positive dimension");
     if (B > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B > 65535");
     const float* o_part = static_cast<const float*>(workspace);
@@ -693,13 +761,59 @@ extern "C" int pli_decode_combine(const void* workspace, void* o, float* lse, in
     dim3 grid(Hq, B);
     const int threads = D >= 128 ? 128 : (D >= 64 ? 64 : 32);
     if (dtype == PLI_F32)
-        decode_combine_kernel<float><<<grid, threads, 0, stream>>>(o_part, lse_part, (float*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1]);
+        decode_combine_kernel<float><<<grid, threads, 0, stream>>>(o_part, lse_part, (float*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1], peer);
     else if (dtype == PLI_BF16)
-        decode_combine_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(o_part, lse_part, (__nv_bfloat16*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1]);
+        decode_combine_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(o_part, lse_part, (__nv_bfloat16*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1], peer);
     else if (dtype == PLI_F16)
-        decode_combine_kernel<__half><<<grid, threads, 0, stream>>>(o_part, lse_part, (__half*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1]);
+        decode_combine_kernel<__half><<<grid, threads, 0, stream>>>(o_part, lse_part, (__half*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1], peer);
     else
         return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}
+
+extern "C" int pli_decode_combine(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
+                                  const int64_t o_strides[2], int dtype, void* stream) {
+    return combine_impl(workspace, o, lse, B, Hq, D, num_splits, o_strides, dtype, stream, PeerScatter{});
+}
+
+extern "C" int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                                      const int32_t* seq_lens, float* lse, int B, int Hq, int Hkv, int D, int max_seq_len,
+                                      int block_size, int table_stride, int layer, int64_t kv_extent,
+                                      const int64_t q_strides[2], const int64_t kv_strides[4], const int64_t o_strides[2],
+                                      float scale, int dtype, int num_splits, void* workspace, size_t workspace_bytes,
+                                      const pli_peer_scatter* ps, void* stream) {
+    if (!ps || !o_strides) return set_error(PLI_ERR_INVALID, "null peer-scatter argument");
+    if (ps->n_peers < 1 || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
+    if (ps->rank < 0 || ps->rank >= ps->n_peers) return set_error(PLI_ERR_INVALID, "rank outside [0, n_peers)");
+    if (!ps->counter) return set_error(PLI_ERR_INVALID, "null completion counter");
+    PeerScatter peer{};
+    for (int r = 0; r < ps->n_peers; ++r) {
+        if (!ps->peer_o[r] || !ps->peer_flags[r]) return set_error(PLI_ERR_INVALID, "null peer pointer for rank %d", r);
+        peer.o[r] = ps->peer_o[r];
+        peer.flags[r] = ps->peer_flags[r];
+    }
+    peer.counter = ps->counter;
+    peer.epoch = ps->epoch;
+    peer.n = ps->n_peers;
+    peer.rank = ps->rank;
+    peer.slice_offset = ps->slice_offset;
+    if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
+    bool wrote_direct = false;
+    // o_direct only selects the direct path; with a peer table the kernel never dereferences it
+    int rc = splitkv_impl(q, k_store, v_store, block_table, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, table_stride,
+                          layer, kv_extent, q_strides, kv_strides, scale, dtype, num_splits, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), ps->peer_o[ps->rank], lse, o_strides, &wrote_direct, &peer);
+    if (rc) return rc;
+    if (wrote_direct) return PLI_OK;
+    return combine_impl(workspace, nullptr, lse, B, Hq, D, num_splits, o_strides, dtype, stream, peer);
+}
+
+extern "C" int pli_peer_wait(const uint32_t* flags, int n_peers, uint32_t epoch, void* stream) {
+    if (!flags) return set_error(PLI_ERR_INVALID, "null flags");
+    if (n_peers < 1 || n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
+    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, n_peers, epoch);
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return PLI_OK;
@@ -718,7 +832,7 @@ extern "C" int pli_decode_fwd(const void* q, const void* k_store, const void* v_
                           static_cast<cudaStream_t>(stream), o, lse, o_strides, &wrote_direct);
     if (rc) return rc;
     if (wrote_direct) return PLI_OK;
-    return pli_decode_combine(workspace, o, lse, B, Hq, D, num_splits, o_strides, dtype, stream);
+    return combine_impl(workspace, o, lse, B, Hq, D, num_splits, o_strides, dtype, stream, PeerScatter{});
 }
 
 extern "C" int pli_kv_append(const void* k_new, const void* v_new, void* k_store, void* v_store, const int32_t* block_table,

@@ -42,6 +42,7 @@ def flash_decode(
     max_seq_len: int | None = None,
     workspace: torch.Tensor | None = None,
     out: torch.Tensor | None = None,
+    peer_out=None,
 ):
     """Attention of one query token per sequence over cached K/V.
 
@@ -50,6 +51,9 @@ def flash_decode(
               tensor (ragged batch; no host sync is made to read it)
     max_seq_len  host upper bound of seq_lens, used to pick the split count; defaults to the int
               seq_lens, else the cache length (contiguous) / table width * page size (paged)
+    peer_out  a `sharding.PeerOutput`: q / caches are this rank's head shard; the kernel stores the shard's output
+              into EVERY rank's full (B_total, Hq_total, D) buffer over NVLink and the call returns that full tensor
+              once all ranks' slices have landed (fused all-gather, no NCCL call).
     Returns o shaped like q (and lse (B, Hq) float32 when return_lse).
     """
     if not (q.is_cuda and k_cache.is_cuda and v_cache.is_cuda):
@@ -130,6 +134,9 @@ def flash_decode(
         workspace = torch.empty(need // 4, dtype=torch.float32, device=dev)
     elif workspace.numel() * workspace.element_size() < need or not workspace.is_cuda:
         raise RuntimeError(f"workspace too small: need {need} bytes")
+    if peer_out is not None:
+        return _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer,
+                               kv_extent, kv_strides, scale, num_splits, workspace, peer_out, return_lse)
     if out is None:
         out = torch.empty((B, Hq, D), dtype=q.dtype, device=dev)
     elif out.shape != (B, Hq, D) or out.dtype != q.dtype or out.stride(-1) != 1:
@@ -145,6 +152,39 @@ def flash_decode(
             workspace.numel() * workspace.element_size(), _lib.current_stream_ptr(dev))
     _lib.check(rc)
     o = out.unsqueeze(2) if q.dim() == 4 else out
+    return (o, lse) if return_lse else o
+
+
+def _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
+                    kv_strides, scale, num_splits, workspace, peer_out, return_lse):
+    sh = peer_out.shard
+    Bt, Ht, Dt = peer_out.shape
+    if (B, Hq, D) != (sh.b_end - sh.b_start, sh.q_end - sh.q_start, Dt) or peer_out.dtype != q3.dtype:
+        raise RuntimeError(f"local decode shape {(B, Hq, D)} / dtype does not match the PeerOutput shard")
+    dev = q3.device
+    lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
+    epoch, idx, bufs = peer_out.begin_step()
+    ps = _lib.PeerScatter()
+    ps.n_peers, ps.rank = sh.world_size, sh.rank
+    for r in range(sh.world_size):
+        ps.peer_o[r] = bufs[r]
+        ps.peer_flags[r] = peer_out.flag_ptrs[r]
+    ps.counter = peer_out.counter_ptr
+    ps.epoch = epoch
+    ps.slice_offset = peer_out.slice_offset
+    lib = _lib.load()
+    import ctypes
+    with _lib.on_device(dev):
+        stream = _lib.current_stream_ptr(dev)
+        rc = lib.pli_decode_fwd_scatter(
+            q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(),
+            lse.data_ptr() if lse is not None else None, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
+            _lib.i64(q3.stride(0), q3.stride(1)), _lib.i64(*kv_strides), _lib.i64(Ht * Dt, Dt), float(scale),
+            _lib.dtype_code(q3.dtype), num_splits, workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+            ctypes.byref(ps), stream)
+        _lib.check(rc)
+        _lib.check(lib.pli_peer_wait(peer_out.flag_ptrs[sh.rank], sh.world_size, epoch, stream))
+    o = peer_out.buffer(idx)
     return (o, lse) if return_lse else o
 
 

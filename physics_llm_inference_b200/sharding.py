@@ -100,6 +100,69 @@ def gather_heads(o_local: torch.Tensor, shard: HeadShard, group=None) -> torch.T
     return buf.reshape(shard.batch, shard.num_heads, *x.shape[2:])
 
 
+class PeerOutput:
+    """Decode output that every rank holds IN FULL, filled by all ranks' decode kernels over NVLink peer memory
+    (`flash_decode(..., peer_out=...)` -> pli_decode_fwd_scatter): the all-gather that would follow a head-sharded
+    decode step is done by the kernel's own stores, and `wait` is one tiny kernel on the stream.
+
+    The buffers live in torch symmetric memory (one allocation per rank, mapped into every process of the group):
+    [flags: 64 words][completion counter][n_buffers x (B, Hq, D)].  Buffers alternate by step so that a rank never
+    overwrites data a slower peer is still reading (see include/pli_attention.h)."""
+
+    def __init__(self, batch: int, num_heads: int, head_dim: int, dtype: torch.dtype, shard: HeadShard, *, group=None,
+                 device=None, n_buffers: int = 2):
+        if shard.world_size > 8:
+            raise ValueError("PeerOutput supports up to 8 ranks (one NVSwitch domain)")
+        self.shard, self.shape, self.dtype = shard, (batch, num_heads, head_dim), dtype
+        self.n_buffers = n_buffers
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        esz = torch.empty((), dtype=dtype).element_size()
+        self.buf_bytes = -(-batch * num_heads * head_dim * esz // 256) * 256
+        self.header_bytes = 512                               # 64 flag words, then the counter at byte 256
+        total = self.header_bytes + n_buffers * self.buf_bytes
+        if shard.world_size > 1:
+            import torch.distributed._symmetric_memory as symm
+            self.storage = symm.empty(total, dtype=torch.uint8, device=self.device)
+            self.storage.zero_()
+            torch.cuda.synchronize(self.device)
+            grp = dist.group.WORLD if group is None else group
+            self.handle = symm.rendezvous(self.storage, grp.group_name)
+            self.base_ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            self.handle.barrier()                             # every rank has zeroed its flags before anyone writes
+        else:
+            self.storage = torch.zeros(total, dtype=torch.uint8, device=self.device)
+            self.handle = None
+            self.base_ptrs = [self.storage.data_ptr()]
+        self.epoch = 0
+
+    def buffer(self, index: int) -> torch.Tensor:
+        """This rank's copy of output buffer `index` as a (B, Hq, D) tensor."""
+        a = self.header_bytes + index * self.buf_bytes
+        n = self.shape[0] * self.shape[1] * self.shape[2]
+        return self.storage[a:a + self.buf_bytes].view(self.dtype)[:n].view(self.shape)
+
+    def begin_step(self):
+        """Advance to the next step: returns (epoch, buffer index, per-rank base pointers of that buffer)."""
+        self.epoch += 1
+        idx = self.epoch % self.n_buffers
+        off = self.header_bytes + idx * self.buf_bytes
+        return self.epoch, idx, [p + off for p in self.base_ptrs]
+
+    @property
+    def flag_ptrs(self):
+        return list(self.base_ptrs)
+
+    @property
+    def counter_ptr(self) -> int:
+        return self.base_ptrs[self.shard.rank] + 256
+
+    @property
+    def slice_offset(self) -> int:
+        """Element offset of this rank's first (batch row, head) inside the full (B, Hq, D) tensor."""
+        _, H, D = self.shape
+        return (self.shard.b_start * H + self.shard.q_start) * D
+
+
 def init_distributed(backend: str | None = None):
     """Join the process group described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (torchrun).
     Returns (rank, world_size, local_rank).  Single-process runs return (0, 1, 0) without a group."""

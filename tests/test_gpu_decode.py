@@ -258,3 +258,21 @@ def test_mixed_prefill_decode_batch():
                                             k.float().cpu(), v.float().cpu(), k.shape[1])
         assert (o[at:at + n].float().cpu().transpose(0, 1) - ro[0]).abs().max().item() <= 2e-2, rid
         at += n
+
+
+@pytest.mark.parametrize("splits", [None, 3])
+def test_decode_peer_output_single_rank(splits):
+    """The fused-gather entry with a world of one: same result as flash_decode, over several steps (buffers
+    alternate by epoch), through both the direct-output kernel and the combine kernel."""
+    B, Hq, Hkv, D, bs, L = 8, 8, 2, 128, 16, 700
+    q, kp, vp, table, lens = orc.seeded_paged(31, B, Hq, Hkv, D, bs, [L] * B, dtype=torch.bfloat16)
+    q, kp, vp, table, lens = q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens.cuda()
+    shard = pli.make_shard(0, 1, Hq, Hkv, B)
+    po = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard)
+    ref = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=splits)[:, :, 0]
+    for step in range(3):
+        o, lse = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=splits, peer_out=po,
+                                  return_lse=True)
+        assert o.shape == (B, Hq, D)
+        assert torch.equal(o, ref), step
+    assert po.epoch == 3

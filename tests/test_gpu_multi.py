@@ -1,0 +1,60 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): head-sharded decode with the output all-gather
+fused into the kernel's peer stores == NCCL gather of the same shards == the unsharded kernel."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+
+    import physics_llm_inference_b200 as pli
+    from oracle import attention_oracle as orc
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    pli.init_distributed("nccl")
+    dev = torch.device("cuda", rank)
+    B, Hq, Hkv, D, bs = 6, 16, 4, 128, 16
+    lens_l = [513, 77, 1024, 300, 16, 999]
+    q, kp, vp, table, lens = orc.seeded_paged(41, B, Hq, Hkv, D, bs, lens_l, dtype=torch.bfloat16)
+    q, kp, vp, table, lens = q.to(dev), kp.to(dev), vp.to(dev), table.to(dev), lens.to(dev)
+    full = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=max(lens_l))[:, :, 0]
+    shard = pli.make_shard(rank, world, Hq, Hkv, B)
+    qs = q[:, shard.q_start:shard.q_end]
+    kps, vps = kp[:, :, :, shard.kv_start:shard.kv_end], vp[:, :, :, shard.kv_start:shard.kv_end]
+    po = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard)
+    ok, why = True, ""
+    for step in range(4):
+        for splits in (None, 2):
+            kw = dict(block_tables=table, max_seq_len=max(lens_l), num_splits=splits)
+            ref = pli.gather_heads(pli.flash_decode(qs, kps, vps, lens, **kw)[:, :, 0], shard)   # NCCL all-gather
+            o = pli.flash_decode(qs, kps, vps, lens, peer_out=po, **kw)                         # fused peer stores
+            if not torch.equal(o, ref):
+                ok, why = False, f"step {step} splits {splits}: fused != gathered, max diff {(o.float() - ref.float()).abs().max().item()}"
+            if (ref.float() - full.float()).abs().max().item() > 1e-2:      # split counts differ: not bit-equal
+                ok, why = False, f"step {step} splits {splits}: sharded != unsharded"
+    if not ok:
+        print(f"[rank {rank}] {why}", flush=True)
+    torch.cuda.synchronize()
+    torch.save(torch.tensor(int(ok)), os.path.join(out_dir, f"ok{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_decode_with_fused_gather(tmp_path):
+    world = 2 if torch.cuda.device_count() < 4 else 4
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert int(torch.load(os.path.join(tmp_path, f"ok{r}.pt"))) == 1
