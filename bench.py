@@ -262,6 +262,8 @@ def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
     # C5: decode B256, paged, ctx sweep
     B, bs = 256, 16
     rows = []
+    shard5 = pli.make_shard(rank, world, Hq, Hkv, B)
+    peer_out = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard5, device=dev) if world > 1 else None
     for L in (1024, 8192, 32768):
         pages = B * L // bs
         kp = torch.empty(pages, 1, bs, hkv_l, D, device=dev, dtype=torch.bfloat16).normal_(generator=g)
@@ -294,6 +296,34 @@ def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
                "kv_bytes_per_gpu": 2 * pages * bs * hkv_l * D * 2, "l2_note": "single pool; >L2 except ctx 1024 at 8 GPUs"}
         if world > 1:
             row["gather_us"] = timed(lambda: pli.gather_heads(od, shard), 2, 10) * 1e3
+            # decode followed by the NCCL all-gather of O, against ONE launch whose stores scatter O to every rank
+            # over NVLink peer memory (+ the flag wait): both leave the full (B, 32, D) output on every rank
+            both = lambda: (fn(), pli.gather_heads(od, shard))  # noqa: E731
+            row["decode_plus_nccl_gather_us"] = timed(both, 2, 10) * 1e3
+            fused = lambda: pli.flash_decode(qd, kp, vp, lens, block_tables=table, max_seq_len=L, workspace=ws,  # noqa: E731
+                                             peer_out=peer_out)
+            row["decode_fused_gather_us"] = timed(fused, 3, 10) * 1e3
+
+            def graphed(step, after=None):
+                g_ = torch.cuda.CUDAGraph()
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    step()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g_):
+                        for _ in range(reps_g):
+                            step()
+                torch.cuda.current_stream(dev).wait_stream(side)
+
+                def replay():
+                    g_.replay()
+                    if after is not None:
+                        after()
+                t = timed(replay, 1, 4 if L < 32768 else 2) / reps_g
+                del g_
+                return t * 1e3
+            row["graph_decode_plus_nccl_gather_us"] = graphed(both)
+            row["graph_decode_fused_gather_us"] = graphed(fused, lambda: peer_out.advance(reps_g))
         rows.append(row)
         del kp, vp
     out["c5_decode_b256"] = {"workload": "C5: paged decode B256, 32q/8kv D128, 16-token pages, KV heads sharded", "sweep": rows}

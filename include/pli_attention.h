@@ -172,22 +172,26 @@ int pli_decode_kernel_kind(int D, int dtype, int block_size, const int64_t kv_st
 /* Decode fused with the all-gather of its output over NVLink / NVSwitch peer memory.  The reference has no
  * collective (ch09/nccl_primitives.py:45-67 only models all-gather cost); a tensor-parallel caller that shards KV
  * heads over ranks (one process per GPU) needs every rank's heads on every rank after the attention block.  Here
- * every rank owns the FULL output (B, Hq_total, D) in peer-mapped memory (CUDA IPC / symmetric memory set up by the
- * host), and a rank's decode kernel stores its slice straight into all of them; the last CTA to finish publishes
- * `epoch` at peer_flags[r][rank] for every r (release, system scope).  pli_peer_wait then makes the stream wait
- * until flags[r] >= epoch for all r, i.e. until every rank's slice has landed in THIS rank's buffer.
+ * every rank owns the FULL output (B, Hq_total, D) in peer-mapped memory (symmetric memory / CUDA IPC set up by the
+ * host), and a rank's decode kernel stores its slice straight into all of them.  pli_peer_publish_wait, launched
+ * behind it on the same stream, publishes the step number at peer_flags[r][rank] for every r (release, system
+ * scope), makes the stream wait until peer_flags[rank][r] has reached it for all r (every rank's slice has landed
+ * HERE) and then advances *epoch.
  *   B, Hq, Hkv and q / kv / workspace describe the LOCAL shard exactly as for pli_decode_fwd;
- *   o_strides {batch, head}: element strides of the full output; slice_offset: element offset of this rank's
- *   first (batch row, head) inside it;  lse (B, Hq) local or NULL;  counter: a zeroed local device word.
- * Buffers may be reused every second step (double-buffer by epoch parity): a rank only passes the wait of epoch e+1
- * after every peer has finished the kernels that read epoch e on its stream. */
+ *   peer_o[r]: output buffer 0 of rank r, buffer 1 follows buffer_stride elements later; o_strides {batch, head}:
+ *   element strides inside one buffer; slice_offset: element offset of this rank's first (batch row, head);
+ *   lse (B, Hq) local or NULL;  peer_flags[r]: rank r's array of n_peers zero-initialised words;
+ *   epoch: LOCAL zero-initialised device word = steps completed.  The step in flight is *epoch + 1 and writes
+ *   buffer (*epoch + 1) & 1; both are read on the device, so the two launches can be captured in a CUDA graph.
+ * Double-buffering by step parity is sufficient: a rank only passes the wait of step e+1 after every peer has
+ * finished, on its stream, the kernels that read the output of step e. */
 #define PLI_MAX_PEERS 8
 typedef struct pli_peer_scatter {
     int32_t n_peers, rank;
     void* peer_o[PLI_MAX_PEERS];
     uint32_t* peer_flags[PLI_MAX_PEERS];
-    uint32_t* counter;
-    uint32_t epoch;
+    uint32_t* epoch;
+    int64_t buffer_stride;
     int64_t slice_offset;
 } pli_peer_scatter;
 int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
@@ -196,7 +200,7 @@ int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_sto
                            const int64_t q_strides[2], const int64_t kv_strides[4], const int64_t o_strides[2],
                            float scale, int dtype, int num_splits, void* workspace, size_t workspace_bytes,
                            const pli_peer_scatter* ps, void* stream);
-int pli_peer_wait(const uint32_t* flags, int n_peers, uint32_t epoch, void* stream);
+int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * KV-cache write path: append n new tokens per sequence.

@@ -150,15 +150,24 @@ __device__ __forceinline__ void mma16816(float* c, uint32_t a0, uint32_t a1, uin
 __device__ __forceinline__ uint32_t sw128(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
 // Fused all-gather of the decode output over NVLink peer memory (pli_decode_fwd_scatter): every rank holds the
-// FULL (B, Hq_total, D) output in peer-mapped memory; a rank's kernel stores its slice into all of them, and the
-// last CTA to finish publishes `epoch` in every rank's flag word for this rank (release at system scope).
+// FULL (B, Hq_total, D) output in peer-mapped memory and a rank's kernel stores its slice into all of them (plain
+// stores, no fence on the hot path).  The kernel boundary completes them; the one-warp peer_publish_wait_kernel
+// that follows on the stream publishes `epoch` in every rank's flag word for this rank (release, system scope) and
+// then waits for every rank's flag here.
+// The step number lives in device memory (*epoch = steps completed; the step in flight is *epoch + 1 and writes
+// output buffer (*epoch + 1) & 1), so a captured CUDA graph replays correctly.
 struct PeerScatter {
-    void* o[PLI_MAX_PEERS];
-    uint32_t* flags[PLI_MAX_PEERS];
-    unsigned int* counter;            // local CTA-completion counter (zero between launches)
-    uint32_t epoch;
-    int n, rank;
+    void* o[PLI_MAX_PEERS];           // buffer 0 of every rank
+    int n;
+    const uint32_t* epoch;
+    int64_t buffer_stride;            // elements from buffer 0 to buffer 1
     int64_t slice_offset;             // element offset of this rank's (batch, head) slice inside the full tensor
+    __device__ __forceinline__ int64_t base() const { return slice_offset + (int64_t)((*epoch + 1u) & 1u) * buffer_stride; }
+};
+struct PeerFlags {
+    uint32_t* flags[PLI_MAX_PEERS];
+    int n, rank;
+    uint32_t* epoch;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -168,17 +177,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-
-// Called by one thread of a CTA after the CTA's peer stores were fenced (__threadfence_system) and the CTA
-// synchronised: the last CTA of the grid publishes the epoch to every rank.
-__device__ __forceinline__ void peer_publish(const PeerScatter& ps, unsigned int total_ctas) {
-    const unsigned int prev = atomicAdd(ps.counter, 1u);
-    if (prev == total_ctas - 1) {
-        __threadfence_system();
-        for (int r = 0; r < ps.n; ++r) st_release_sys(ps.flags[r] + ps.rank, ps.epoch);
-        *ps.counter = 0u;             // the next launch on this stream starts from zero
-    }
 }
 
 struct DecodeTmaParams {
@@ -430,7 +428,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             const float o_val = den > 0.f ? o / den : 0.f;
             const float lse_val = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
             if (p.peer.n > 0) {
-                const int64_t off = p.peer.slice_offset + b * p.osb + (h_base + row) * p.osh + d;
+                const int64_t off = p.peer.base() + b * p.osb + (h_base + row) * p.osh + d;
                 const elem_t val = from_f32<elem_t>(o_val);
                 for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[off] = val;
                 if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val;
@@ -443,11 +441,6 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 p.o_part[prow * kD + d] = o_val;
                 if (d == 0) p.lse_part[prow] = lse_val;
             }
-        }
-        if (p.peer.n > 0) {
-            __threadfence_system();
-            named_bar_sync(1, kConsumerWarps * 32);
-            if (threadIdx.x == 0) peer_publish(p.peer, gridDim.x * gridDim.y * gridDim.z);
         }
     }
 }
@@ -479,30 +472,34 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __rest
         }
         const T val = from_f32<T>(acc * inv);
         if (peer.n > 0) {
-            const int64_t off = peer.slice_offset + b * osb + h * osh + d;
+            const int64_t off = peer.base() + b * osb + h * osh + d;
             for (int r = 0; r < peer.n; ++r) reinterpret_cast<T*>(peer.o[r])[off] = val;
         } else {
             o[b * osb + h * osh + d] = val;
         }
     }
     if (lse != nullptr && threadIdx.x == 0) lse[(int64_t)b * Hq + h] = den > 0.f ? M + logf(den) : -INFINITY;
-    if (peer.n > 0) {
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0) peer_publish(peer, gridDim.x * gridDim.y);
-    }
 }
 
-// One thread per rank spins (acquire, system scope) until that rank's slice of `epoch` has landed here.  The
-// producers never wait on anybody, so this cannot deadlock; a lost peer traps after ~4 s instead of hanging.
-__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t epoch) {
+// Runs after the scattering kernel on the same stream (whose peer stores are complete at the kernel boundary).
+// Thread r tells rank r that this rank's slice of `epoch` has landed (release, system scope), then spins (acquire)
+// until rank r's slice has landed here.  Publishing never waits on anybody, so this cannot deadlock; a lost peer
+// traps after ~4 s instead of hanging.
+__global__ void peer_publish_wait_kernel(const PeerFlags pf) {
     const int r = threadIdx.x;
-    if (r >= n) return;
-    for (long long spin = 0;; ++spin) {
-        if ((int32_t)(ld_acquire_sys(flags + r) - epoch) >= 0) return;
-        __nanosleep(64);
-        if (spin > (1ll << 25)) __trap();
+    const uint32_t e = *pf.epoch + 1u;
+    __syncwarp();
+    if (r < pf.n) {
+        __threadfence_system();
+        st_release_sys(pf.flags[r] + pf.rank, e);
+        const uint32_t* mine = pf.flags[pf.rank] + r;
+        for (long long spin = 0; (int32_t)(ld_acquire_sys(mine) - e) < 0; ++spin) {
+            __nanosleep(32);
+            if (spin > (1ll << 26)) __trap();
+        }
     }
+    __syncwarp();
+    if (r == 0) *pf.epoch = e;        // the step is complete on this rank
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -787,17 +784,15 @@ extern "C" int pli_decode_fwd_scatter(const void* q, const void* k_store, const 
     if (!ps || !o_strides) return set_error(PLI_ERR_INVALID, "null peer-scatter argument");
     if (ps->n_peers < 1 || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
     if (ps->rank < 0 || ps->rank >= ps->n_peers) return set_error(PLI_ERR_INVALID, "rank outside [0, n_peers)");
-    if (!ps->counter) return set_error(PLI_ERR_INVALID, "null completion counter");
     PeerScatter peer{};
     for (int r = 0; r < ps->n_peers; ++r) {
-        if (!ps->peer_o[r] || !ps->peer_flags[r]) return set_error(PLI_ERR_INVALID, "null peer pointer for rank %d", r);
+        if (!ps->peer_o[r]) return set_error(PLI_ERR_INVALID, "null peer pointer for rank %d", r);
         peer.o[r] = ps->peer_o[r];
-        peer.flags[r] = ps->peer_flags[r];
     }
-    peer.counter = ps->counter;
-    peer.epoch = ps->epoch;
+    if (!ps->epoch) return set_error(PLI_ERR_INVALID, "null epoch word");
     peer.n = ps->n_peers;
-    peer.rank = ps->rank;
+    peer.epoch = ps->epoch;
+    peer.buffer_stride = ps->buffer_stride;
     peer.slice_offset = ps->slice_offset;
     if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
     bool wrote_direct = false;
@@ -810,10 +805,20 @@ extern "C" int pli_decode_fwd_scatter(const void* q, const void* k_store, const 
     return combine_impl(workspace, nullptr, lse, B, Hq, D, num_splits, o_strides, dtype, stream, peer);
 }
 
-extern "C" int pli_peer_wait(const uint32_t* flags, int n_peers, uint32_t epoch, void* stream) {
-    if (!flags) return set_error(PLI_ERR_INVALID, "null flags");
-    if (n_peers < 1 || n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
-    peer_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(flags, n_peers, epoch);
+extern "C" int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream) {
+    if (!ps) return set_error(PLI_ERR_INVALID, "null peer-scatter argument");
+    if (ps->n_peers < 1 || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
+    if (ps->rank < 0 || ps->rank >= ps->n_peers) return set_error(PLI_ERR_INVALID, "rank outside [0, n_peers)");
+    PeerFlags pf{};
+    for (int r = 0; r < ps->n_peers; ++r) {
+        if (!ps->peer_flags[r]) return set_error(PLI_ERR_INVALID, "null flag pointer for rank %d", r);
+        pf.flags[r] = ps->peer_flags[r];
+    }
+    if (!ps->epoch) return set_error(PLI_ERR_INVALID, "null epoch word");
+    pf.n = ps->n_peers;
+    pf.rank = ps->rank;
+    pf.epoch = ps->epoch;
+    peer_publish_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf);
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return PLI_OK;

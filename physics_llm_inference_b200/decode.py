@@ -163,14 +163,13 @@ def _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_se
         raise RuntimeError(f"local decode shape {(B, Hq, D)} / dtype does not match the PeerOutput shard")
     dev = q3.device
     lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
-    epoch, idx, bufs = peer_out.begin_step()
     ps = _lib.PeerScatter()
     ps.n_peers, ps.rank = sh.world_size, sh.rank
     for r in range(sh.world_size):
-        ps.peer_o[r] = bufs[r]
+        ps.peer_o[r] = peer_out.output_ptrs[r]
         ps.peer_flags[r] = peer_out.flag_ptrs[r]
-    ps.counter = peer_out.counter_ptr
-    ps.epoch = epoch
+    ps.epoch = peer_out.epoch_ptr
+    ps.buffer_stride = peer_out.buffer_stride
     ps.slice_offset = peer_out.slice_offset
     lib = _lib.load()
     import ctypes
@@ -183,8 +182,9 @@ def _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_se
             _lib.dtype_code(q3.dtype), num_splits, workspace.data_ptr(), workspace.numel() * workspace.element_size(),
             ctypes.byref(ps), stream)
         _lib.check(rc)
-        _lib.check(lib.pli_peer_wait(peer_out.flag_ptrs[sh.rank], sh.world_size, epoch, stream))
-    o = peer_out.buffer(idx)
+        _lib.check(lib.pli_peer_publish_wait(ctypes.byref(ps), stream))
+    # under stream capture nothing ran yet: the caller accounts for replays with peer_out.advance()
+    o = peer_out.buffer((peer_out.epoch + 1) & 1) if torch.cuda.is_current_stream_capturing() else peer_out.advance()
     return (o, lse) if return_lse else o
 
 

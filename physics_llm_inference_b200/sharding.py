@@ -102,24 +102,25 @@ def gather_heads(o_local: torch.Tensor, shard: HeadShard, group=None) -> torch.T
 
 class PeerOutput:
     """Decode output that every rank holds IN FULL, filled by all ranks' decode kernels over NVLink peer memory
-    (`flash_decode(..., peer_out=...)` -> pli_decode_fwd_scatter): the all-gather that would follow a head-sharded
-    decode step is done by the kernel's own stores, and `wait` is one tiny kernel on the stream.
+    (`flash_decode(..., peer_out=...)` -> pli_decode_fwd_scatter + pli_peer_publish_wait): the all-gather that
+    would follow a head-sharded decode step is done by the kernel's own stores.
 
     The buffers live in torch symmetric memory (one allocation per rank, mapped into every process of the group):
-    [flags: 64 words][completion counter][n_buffers x (B, Hq, D)].  Buffers alternate by step so that a rank never
+    [flag words, one per rank | step counter at byte 256 | pad to 512][buffer 0 (B, Hq, D)][buffer 1].
+    The step counter is read on the device, so the step can be captured in a CUDA graph; `epoch` mirrors it on
+    the host (call `advance()` after replaying a captured step).  Step e writes buffer e & 1, so a rank never
     overwrites data a slower peer is still reading (see include/pli_attention.h)."""
 
     def __init__(self, batch: int, num_heads: int, head_dim: int, dtype: torch.dtype, shard: HeadShard, *, group=None,
-                 device=None, n_buffers: int = 2):
+                 device=None):
         if shard.world_size > 8:
             raise ValueError("PeerOutput supports up to 8 ranks (one NVSwitch domain)")
         self.shard, self.shape, self.dtype = shard, (batch, num_heads, head_dim), dtype
-        self.n_buffers = n_buffers
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        esz = torch.empty((), dtype=dtype).element_size()
-        self.buf_bytes = -(-batch * num_heads * head_dim * esz // 256) * 256
-        self.header_bytes = 512                               # 64 flag words, then the counter at byte 256
-        total = self.header_bytes + n_buffers * self.buf_bytes
+        self.esz = torch.empty((), dtype=dtype).element_size()
+        self.buf_bytes = -(-batch * num_heads * head_dim * self.esz // 256) * 256
+        self.header_bytes = 512
+        total = self.header_bytes + 2 * self.buf_bytes
         if shard.world_size > 1:
             import torch.distributed._symmetric_memory as symm
             self.storage = symm.empty(total, dtype=torch.uint8, device=self.device)
@@ -133,7 +134,7 @@ class PeerOutput:
             self.storage = torch.zeros(total, dtype=torch.uint8, device=self.device)
             self.handle = None
             self.base_ptrs = [self.storage.data_ptr()]
-        self.epoch = 0
+        self.epoch = 0                                        # host mirror of the device step counter
 
     def buffer(self, index: int) -> torch.Tensor:
         """This rank's copy of output buffer `index` as a (B, Hq, D) tensor."""
@@ -141,20 +142,27 @@ class PeerOutput:
         n = self.shape[0] * self.shape[1] * self.shape[2]
         return self.storage[a:a + self.buf_bytes].view(self.dtype)[:n].view(self.shape)
 
-    def begin_step(self):
-        """Advance to the next step: returns (epoch, buffer index, per-rank base pointers of that buffer)."""
-        self.epoch += 1
-        idx = self.epoch % self.n_buffers
-        off = self.header_bytes + idx * self.buf_bytes
-        return self.epoch, idx, [p + off for p in self.base_ptrs]
+    def advance(self, steps: int = 1) -> torch.Tensor:
+        """Account for `steps` steps launched on the device (a direct call does this itself; call it after replaying
+        a CUDA graph that holds captured steps).  Returns the buffer of the latest step."""
+        self.epoch += steps
+        return self.buffer(self.epoch & 1)
+
+    @property
+    def output_ptrs(self):
+        return [p + self.header_bytes for p in self.base_ptrs]
 
     @property
     def flag_ptrs(self):
         return list(self.base_ptrs)
 
     @property
-    def counter_ptr(self) -> int:
+    def epoch_ptr(self) -> int:
         return self.base_ptrs[self.shard.rank] + 256
+
+    @property
+    def buffer_stride(self) -> int:
+        return self.buf_bytes // self.esz
 
     @property
     def slice_offset(self) -> int:

@@ -44,6 +44,25 @@ def _worker(rank, world, port, out_dir):
                 ok, why = False, f"step {step} splits {splits}: fused != gathered, max diff {(o.float() - ref.float()).abs().max().item()}"
             if (ref.float() - full.float()).abs().max().item() > 1e-2:      # split counts differ: not bit-equal
                 ok, why = False, f"step {step} splits {splits}: sharded != unsharded"
+    # the same step captured in a CUDA graph (the step counter and the buffer parity are read on the device)
+    kw = dict(block_tables=table, max_seq_len=max(lens_l))
+    ref = pli.gather_heads(pli.flash_decode(qs, kps, vps, lens, **kw)[:, :, 0], shard)
+    ws = pli.decode_workspace(qs.shape[0], qs.shape[1], D, pli.decode_num_splits(qs.shape[0], kps.shape[3], max(lens_l)), dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        pli.flash_decode(qs, kps, vps, lens, peer_out=po, workspace=ws, **kw)          # warm-up outside the graph
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph):
+            pli.flash_decode(qs, kps, vps, lens, peer_out=po, workspace=ws, **kw)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    for rep in range(3):
+        graph.replay()
+        o = po.advance()
+        torch.cuda.synchronize()
+        if not torch.equal(o, ref):
+            ok, why = False, f"graph replay {rep}: fused != gathered"
     if not ok:
         print(f"[rank {rank}] {why}", flush=True)
     torch.cuda.synchronize()
