@@ -256,6 +256,14 @@ def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
         o = pli.flash_attention_forward(q, k, v, causal=True)
         entry["gather_ms"] = timed(lambda: pli.gather_heads(o, shard), 1, 3)
         entry["gather_bytes_total"] = Hq * N * D * 2
+        # prefill followed by the NCCL all-gather of O, against the kernel whose epilogue TMA-stores every O tile to
+        # all ranks over NVLink (+ flag wait): both leave the full (1, 32, N, D) output on every rank
+        entry["prefill_plus_nccl_gather_ms"] = timed(
+            lambda: pli.gather_heads(pli.flash_attention_forward(q, k, v, causal=True), shard), 1, 3)
+        po4 = pli.PeerOutput(1, Hq, D, torch.bfloat16, shard, device=dev, seq_len=N)
+        entry["prefill_fused_gather_ms"] = timed(
+            lambda: pli.flash_attention_forward(q, k, v, causal=True, peer_out=po4), 2, 5)
+        del po4
     out["c4_prefill_65536"] = entry
     del q, k, v
 

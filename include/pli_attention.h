@@ -202,6 +202,17 @@ int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_sto
                            const pli_peer_scatter* ps, void* stream);
 int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream);
 
+/* Prefill with the same fused all-gather: the epilogue's TMA store of every finished O tile goes to all ranks'
+ * full outputs (B_total, Hq_total, Nq, D), so the transfer overlaps the MMAs of the following tiles; follow it with
+ * pli_peer_publish_wait.  q/k/v/lse and B, Hq, Hkv describe the LOCAL shard as for pli_prefill_fwd; o_strides
+ * {batch, head, token} are those of the full output; the shard's first batch row / q head inside it are
+ * batch_offset / head_offset (ps->slice_offset is not used).  bf16/f16, head_dim 64/128 only. */
+int pli_prefill_fwd_scatter(const void* q, const void* k, const void* v, float* lse, int B, int Hq, int Hkv,
+                            int Nq, int Nk, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                            const int64_t v_strides[3], const int64_t o_strides[3], float scale, int causal,
+                            int dtype, int B_total, int Hq_total, int batch_offset, int head_offset,
+                            const pli_peer_scatter* ps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * KV-cache write path: append n new tokens per sequence.
  *

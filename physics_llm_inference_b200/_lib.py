@@ -59,6 +59,9 @@ _SIGNATURES = {
     "pli_decode_fwd_scatter": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_float, C.c_int,
                                          C.c_int, _VP, C.c_size_t, C.POINTER(PeerScatter), _VP]),
+    "pli_prefill_fwd_scatter": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          _I64P, _I64P, _I64P, _I64P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.POINTER(PeerScatter), _VP]),
     "pli_peer_publish_wait": (C.c_int, [C.POINTER(PeerScatter), _VP]),
     "pli_kv_append": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, _I64P, _I64P, C.c_int, _VP]),

@@ -48,10 +48,17 @@ int launch_prefill_simt(const void* q, const void* k, const void* v, void* o, fl
                         int Hkv, int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks,
                         const int64_t* vs, const int64_t* os, float scale, int causal, int dtype,
                         cudaStream_t stream);
-int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq,
-                           int Hkv, int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks,
-                           const int64_t* vs, const int64_t* os, float scale, int causal, int dtype,
-                           cudaStream_t stream);
+// peer-scatter description for the prefill launcher (see pli_prefill_fwd_scatter)
+struct PrefillPeerInfo {
+    void* o[PLI_MAX_PEERS];      // buffer 0 of every rank's full output
+    const uint32_t* epoch;
+    int64_t buffer_stride;       // elements between buffer 0 and buffer 1
+    int n, Hq_total, B_total, head_offset, batch_offset;
+};
+int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv,
+                           int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks, const int64_t* vs,
+                           const int64_t* os, float scale, int causal, int dtype, cudaStream_t stream,
+                           const PrefillPeerInfo* peer = nullptr);
 int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table,
                                  const int32_t* seq_lens, const int32_t* cu_seqlens_q, int64_t total_q, void* o, float* lse,
                                  int B, int Hq, int Hkv, int Nq, int D, int max_seq_len, int block_size, int table_stride,

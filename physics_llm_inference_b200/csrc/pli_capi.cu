@@ -143,6 +143,46 @@ extern "C" int pli_prefill_fwd(const void* q, const void* k, const void* v, void
                                causal, dtype, stream);
 }
 
+extern "C" int pli_prefill_fwd_scatter(const void* q, const void* k, const void* v, float* lse, int B, int Hq, int Hkv,
+                                       int Nq, int Nk, int D, const int64_t q_strides[3], const int64_t k_strides[3],
+                                       const int64_t v_strides[3], const int64_t o_strides[3], float scale, int causal,
+                                       int dtype, int B_total, int Hq_total, int batch_offset, int head_offset,
+                                       const pli_peer_scatter* ps, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!q || !k || !v || !ps) return set_error(PLI_ERR_INVALID, "null pointer argument");
+    if (!q_strides || !k_strides || !v_strides || !o_strides) return set_error(PLI_ERR_INVALID, "null stride array");
+    if (B <= 0 || Hq <= 0 || Hkv <= 0 || Nq <= 0 || Nk <= 0 || D <= 0)
+        return set_error(PLI_ERR_INVALID, "non-positive dimension (B=%d Hq=%d Hkv=%d Nq=%d Nk=%d D=%d)", B, Hq, Hkv, Nq, Nk, D);
+    if (Hq % Hkv != 0) return set_error(PLI_ERR_INVALID, "Hq (%d) must be a multiple of Hkv (%d)", Hq, Hkv);
+    if (causal && Nq > Nk) return set_error(PLI_ERR_INVALID, "causal attention needs Nq <= Nk (got %d > %d)", Nq, Nk);
+    if (ps->n_peers < 1 || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
+    if (ps->rank < 0 || ps->rank >= ps->n_peers) return set_error(PLI_ERR_INVALID, "rank outside [0, n_peers)");
+    if (!ps->epoch) return set_error(PLI_ERR_INVALID, "null epoch word");
+    if (batch_offset < 0 || head_offset < 0 || batch_offset + B > B_total || head_offset + Hq > Hq_total)
+        return set_error(PLI_ERR_INVALID, "the local (batch, head) slice does not fit the full output");
+    if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "current CUDA device is not sm_100 (B200)");
+    if (!(scale > 0.f)) return set_error(PLI_ERR_UNSUPPORTED, "the scatter entry needs scale > 0");
+    PrefillPeerInfo info{};
+    for (int r = 0; r < ps->n_peers; ++r) {
+        if (!ps->peer_o[r]) return set_error(PLI_ERR_INVALID, "null peer pointer for rank %d", r);
+        if ((reinterpret_cast<uintptr_t>(ps->peer_o[r]) & 15) || (ps->buffer_stride % 8))
+            return set_error(PLI_ERR_INVALID, "peer buffers must be 16-byte aligned");
+        info.o[r] = ps->peer_o[r];
+    }
+    if (!tcgen05_eligible(D, dtype, q_strides, k_strides, v_strides, o_strides, q, k, v, ps->peer_o[ps->rank]))
+        return set_error(PLI_ERR_UNSUPPORTED, "the scatter entry serves the tcgen05 kernel only (bf16/f16, head_dim 64/128, "
+                                               "16-byte aligned, strides multiple of 8)");
+    info.epoch = ps->epoch;
+    info.buffer_stride = ps->buffer_stride;
+    info.n = ps->n_peers;
+    info.Hq_total = Hq_total;
+    info.B_total = B_total;
+    info.head_offset = head_offset;
+    info.batch_offset = batch_offset;
+    return launch_prefill_tcgen05(q, k, v, ps->peer_o[ps->rank], lse, B, Hq, Hkv, Nq, Nk, D, q_strides, k_strides,
+                                  v_strides, o_strides, scale, causal, dtype, stream, &info);
+}
+
 extern "C" int pli_prefill_paged_fwd(const void* q, const void* k_pool, const void* v_pool, const int32_t* block_table,
                                      const int32_t* seq_lens, void* o, float* lse, int B, int Hq, int Hkv, int Nq, int D,
                                      int max_seq_len, int block_size, int table_stride, int layer, int64_t num_pages,

@@ -19,6 +19,7 @@
 // sub-tile; every tile is stored as D/64 sub-tiles of [128 rows][64 el] with the 128-byte swizzle
 // that TMA and UMMA share.
 #include <cstdlib>
+#include <cstring>
 #include <type_traits>
 
 #include "common.cuh"
@@ -86,6 +87,16 @@ struct PrefillParams {
     uint8_t* o_base;                  // raw o pointer + element strides for the predicated store of ragged tiles
     int64_t o_st_tok, o_st_head;
     int64_t lse_sb, lse_sh;           // lse index = b * lse_sb + h * lse_sh + (row inside the q tensor)
+};
+
+// Fused all-gather of O over NVLink peer memory (pli_prefill_fwd_scatter): every rank holds the FULL
+// (B_total, Hq_total, Nq, D) output twice (double-buffered by step parity) in peer-mapped memory; the epilogue's TMA
+// store of each finished O sub-tile is issued once per rank, into the buffer (*epoch + 1) & 1 of that rank, so the
+// transfer rides behind the MMAs of the following tiles.  n == 0: plain local store through map_o.
+struct PeerMaps {
+    CUtensorMap maps[2][PLI_MAX_PEERS];   // [buffer][rank]: 4-D maps over the full output of that rank
+    const uint32_t* epoch;
+    int n, head_offset, batch_offset;
 };
 
 // CTA 0 timeline: each tracing warp owns region `region` of the buffer and keeps its own cursor in a
@@ -189,7 +200,7 @@ template <int kD, bool kBf16, int kCluster, bool kPaged>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
-                       const PrefillParams p) {
+                       const PrefillParams p, const __grid_constant__ PeerMaps peers) {
     using L = SmemLayout<kD>;
     constexpr int kStages = L::kKVStages;
     constexpr int kTileBytes = L::kTileBytes;
@@ -369,6 +380,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int row = wq * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
         uint32_t sc_par = 0, item_cnt = 0;                // sc_par bit t*2+h: phase parity of sc_full[t*2+h]
+        int peer_buf = 0;
+        if constexpr (!kPaged) {
+            if (peers.n > 0) peer_buf = (int)((*peers.epoch + 1u) & 1u);
+        }
         uint32_t sf_base = 0;                             // bit t*2+h: parity of s_full[t*2+h]'s first phase in this item
         if (lane == 0) {                                  // first item: O_0 / O_1 are free
             mbar_arrive(&pv_ok[0]);
@@ -470,7 +485,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         fence_proxy_async();
                         named_bar_sync(kBarEpilogue, 128);
                         if (warp == 8 && lane == 0 && q_tile0 < it.nq) {
-                            tma_store_4d(&map_o, sO, hf * 64, it.qbase + q_tile0, it.h[t], it.bq);
+                            if (kPaged || peers.n == 0) {
+                                tma_store_4d(&map_o, sO, hf * 64, it.qbase + q_tile0, it.h[t], it.bq);
+                            } else {
+                                for (int r = 0; r < peers.n; ++r)
+                                    tma_store_4d(&peers.maps[peer_buf][r], sO, hf * 64, q_tile0, it.h[t] + peers.head_offset,
+                                                 it.b + peers.batch_offset);
+                            }
                             tma_store_commit();
                         }
                     }
@@ -799,9 +820,18 @@ int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int
     return PLI_OK;
 }
 
+const PeerMaps& no_peers() {
+    static const PeerMaps none = [] {
+        PeerMaps m;
+        memset(&m, 0, sizeof(m));
+        return m;
+    }();
+    return none;
+}
+
 template <int kD, bool kBf16, int kCluster, bool kPaged = false>
 int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
-             const PrefillParams& p, cudaStream_t stream) {
+             const PrefillParams& p, cudaStream_t stream, const PeerMaps& peers = no_peers()) {
     auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster, kPaged>;
     const int smem = SmemLayout<kD>::kTotal + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
@@ -821,7 +851,7 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mo, p));
+    PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mo, p, peers));
     count_launch();
     return PLI_OK;
 }
@@ -925,9 +955,23 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
 
 int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq, int Hkv,
                            int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks, const int64_t* vs,
-                           const int64_t* os, float scale, int causal, int dtype, cudaStream_t stream) {
+                           const int64_t* os, float scale, int causal, int dtype, cudaStream_t stream,
+                           const PrefillPeerInfo* peer) {
     CUtensorMap mq, mk, mv, mo;
     int rc;
+    PeerMaps pm = no_peers();
+    if (peer != nullptr) {
+        // os = strides of the FULL output {batch, head, token}; o = this rank's buffer 0 (only used for the local map)
+        for (int buf = 0; buf < 2; ++buf)
+            for (int r = 0; r < peer->n; ++r) {
+                const char* base = static_cast<const char*>(peer->o[r]) + (size_t)buf * peer->buffer_stride * 2;
+                if ((rc = make_map_4d(&pm.maps[buf][r], base, dtype, D, Nq, peer->Hq_total, peer->B_total, os))) return rc;
+            }
+        pm.epoch = peer->epoch;
+        pm.n = peer->n;
+        pm.head_offset = peer->head_offset;
+        pm.batch_offset = peer->batch_offset;
+    }
     if ((rc = make_map_4d(&mq, q, dtype, D, Nq, Hq, B, qs))) return rc;
     // CTA pairs share K/V when consecutive items are two q heads of one KV group (even group size): each CTA
     // then loads 64-row halves of the K/V tiles and multicasts them
@@ -936,7 +980,8 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
     if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pairs ? kHN : kBN))) return rc;
     if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pairs ? kHN : kBN))) return rc;
-    if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
+    if (peer != nullptr) mo = pm.maps[0][0];
+    else if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
     PrefillParams p;
     p.lse = lse;
     p.B = B;
@@ -951,7 +996,7 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     if (p.total_items < 0) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
     const bool bf16 = dtype == PLI_BF16;
 #define PLI_GO(DD, BF)                                                                            \
-    return pairs ? launch_t<DD, BF, 2>(mq, mk, mv, mo, p, stream) : launch_t<DD, BF, 1>(mq, mk, mv, mo, p, stream)
+    return pairs ? launch_t<DD, BF, 2>(mq, mk, mv, mo, p, stream, pm) : launch_t<DD, BF, 1>(mq, mk, mv, mo, p, stream, pm)
     if (D == 128) {
         if (bf16) PLI_GO(128, true);
         PLI_GO(128, false);

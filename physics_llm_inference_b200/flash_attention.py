@@ -71,8 +71,13 @@ def flash_attention_forward(
     *,
     causal: bool = False,
     return_lse: bool = False,
+    peer_out=None,
 ):
-    """softmax(Q K^T * scale [+ causal mask]) V on the GPU; see the module docstring."""
+    """softmax(Q K^T * scale [+ causal mask]) V on the GPU; see the module docstring.
+
+    peer_out (a `sharding.PeerOutput` built with seq_len=Nq): q, k, v are this rank's head shard; every finished O
+    tile is TMA-stored into ALL ranks' full (B, Hq_total, Nq, D) buffers over NVLink, and the call returns that
+    full tensor once every rank's tiles have landed (all-gather fused into the kernel, no NCCL call)."""
     if config is None:
         config = FlashAttentionConfig()
     _check_inputs(q, k, v)
@@ -83,12 +88,38 @@ def flash_attention_forward(
     if scale is None:
         scale = D ** -0.5
     q, k, v = _unit_inner(q), _unit_inner(k), _unit_inner(v)
+    lse = torch.empty((B, Hq, Nq), dtype=torch.float32, device=q.device) if return_lse else None
+    lib = _lib.load()
+    if peer_out is not None:
+        import ctypes
+        sh = peer_out.shard
+        if len(peer_out.shape) != 4 or peer_out.dtype != q.dtype or \
+                (B, Hq, Nq, D) != (sh.b_end - sh.b_start, sh.q_end - sh.q_start, peer_out.shape[2], peer_out.shape[3]):
+            raise RuntimeError(f"local q {tuple(q.shape)} / dtype does not match the PeerOutput shard {peer_out.shape}")
+        Bt, Ht, _, _ = peer_out.shape
+        ps = _lib.PeerScatter()
+        ps.n_peers, ps.rank = sh.world_size, sh.rank
+        for r in range(sh.world_size):
+            ps.peer_o[r] = peer_out.output_ptrs[r]
+            ps.peer_flags[r] = peer_out.flag_ptrs[r]
+        ps.epoch = peer_out.epoch_ptr
+        ps.buffer_stride = peer_out.buffer_stride
+        ps.slice_offset = peer_out.slice_offset
+        with _lib.on_device(q.device):
+            stream = _lib.current_stream_ptr(q.device)
+            rc = lib.pli_prefill_fwd_scatter(
+                q.data_ptr(), k.data_ptr(), v.data_ptr(), lse.data_ptr() if lse is not None else None, B, Hq, Hkv, Nq, Nk,
+                D, _lib.i64(*q.stride()[:3]), _lib.i64(*k.stride()[:3]), _lib.i64(*v.stride()[:3]),
+                _lib.i64(Ht * Nq * D, Nq * D, D), float(scale), int(bool(causal)), _lib.dtype_code(q.dtype), Bt, Ht,
+                sh.b_start, sh.q_start, ctypes.byref(ps), stream)
+            _lib.check(rc)
+            _lib.check(lib.pli_peer_publish_wait(ctypes.byref(ps), stream))
+        o = peer_out.buffer((peer_out.epoch + 1) & 1) if torch.cuda.is_current_stream_capturing() else peer_out.advance()
+        return (o, lse) if return_lse else o
     out = torch.empty_like(q)
     if out.stride(-1) != 1:
         out = torch.empty(q.shape, dtype=q.dtype, device=q.device)
-    lse = torch.empty((B, Hq, Nq), dtype=torch.float32, device=q.device) if return_lse else None
 
-    lib = _lib.load()
     with _lib.on_device(q.device):
         rc = lib.pli_prefill_fwd(
             q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), lse.data_ptr() if lse is not None else None,

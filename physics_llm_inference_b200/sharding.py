@@ -112,13 +112,16 @@ class PeerOutput:
     overwrites data a slower peer is still reading (see include/pli_attention.h)."""
 
     def __init__(self, batch: int, num_heads: int, head_dim: int, dtype: torch.dtype, shard: HeadShard, *, group=None,
-                 device=None):
+                 device=None, seq_len: int | None = None):
+        """Output of a decode step (B, Hq, D), or with `seq_len` of a prefill call (B, Hq, seq_len, D)."""
         if shard.world_size > 8:
             raise ValueError("PeerOutput supports up to 8 ranks (one NVSwitch domain)")
-        self.shard, self.shape, self.dtype = shard, (batch, num_heads, head_dim), dtype
+        self.shard, self.dtype = shard, dtype
+        self.shape = (batch, num_heads, head_dim) if seq_len is None else (batch, num_heads, seq_len, head_dim)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.esz = torch.empty((), dtype=dtype).element_size()
-        self.buf_bytes = -(-batch * num_heads * head_dim * self.esz // 256) * 256
+        self.numel = batch * num_heads * head_dim * (1 if seq_len is None else seq_len)
+        self.buf_bytes = -(-self.numel * self.esz // 256) * 256
         self.header_bytes = 512
         total = self.header_bytes + 2 * self.buf_bytes
         if shard.world_size > 1:
@@ -137,10 +140,9 @@ class PeerOutput:
         self.epoch = 0                                        # host mirror of the device step counter
 
     def buffer(self, index: int) -> torch.Tensor:
-        """This rank's copy of output buffer `index` as a (B, Hq, D) tensor."""
+        """This rank's copy of output buffer `index`, shaped (B, Hq, D) or (B, Hq, N, D)."""
         a = self.header_bytes + index * self.buf_bytes
-        n = self.shape[0] * self.shape[1] * self.shape[2]
-        return self.storage[a:a + self.buf_bytes].view(self.dtype)[:n].view(self.shape)
+        return self.storage[a:a + self.buf_bytes].view(self.dtype)[:self.numel].view(self.shape)
 
     def advance(self, steps: int = 1) -> torch.Tensor:
         """Account for `steps` steps launched on the device (a direct call does this itself; call it after replaying
@@ -166,9 +168,9 @@ class PeerOutput:
 
     @property
     def slice_offset(self) -> int:
-        """Element offset of this rank's first (batch row, head) inside the full (B, Hq, D) tensor."""
-        _, H, D = self.shape
-        return (self.shard.b_start * H + self.shard.q_start) * D
+        """Element offset of this rank's first (batch row, head) inside the full tensor."""
+        per_head = self.numel // (self.shape[0] * self.shape[1])
+        return (self.shard.b_start * self.shape[1] + self.shard.q_start) * per_head
 
 
 def init_distributed(backend: str | None = None):

@@ -63,6 +63,18 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         if not torch.equal(o, ref):
             ok, why = False, f"graph replay {rep}: fused != gathered"
+    # prefill: O tiles TMA-stored into every rank's full output
+    Bp, N = 2, 640
+    qf, kf, vf = orc.seeded_qkv(43, Bp, Hq, Hkv, N, N, D)
+    qf, kf, vf = qf.to(dev).bfloat16(), kf.to(dev).bfloat16(), vf.to(dev).bfloat16()
+    shp = pli.make_shard(rank, world, Hq, Hkv, Bp)
+    qs2, ks2, vs2 = pli.shard_kv_heads(qf, kf, vf, shp)
+    ref = pli.gather_heads(pli.flash_attention_forward(qs2, ks2, vs2, causal=True), shp)
+    pop = pli.PeerOutput(Bp, Hq, D, torch.bfloat16, shp, seq_len=N)
+    for step in range(3):
+        o = pli.flash_attention_forward(qs2, ks2, vs2, causal=True, peer_out=pop)
+        if o.shape != ref.shape or not torch.equal(o, ref):
+            ok, why = False, f"prefill step {step}: fused != gathered"
     if not ok:
         print(f"[rank {rank}] {why}", flush=True)
     torch.cuda.synchronize()

@@ -293,3 +293,17 @@ def test_varlen_paged_prefill_parity(bs, D, Hkv, G, q_lens, lens):
         ro, rlse = orc.paged_decode_oracle(qb, kp, vp, table[b:b + 1], lens_t[b:b + 1], layer=1)
         assert (o[a:e].float().cpu().transpose(0, 1) - ro[0]).abs().max().item() <= 2e-2, b
         assert (lse[:, a:e].cpu() - rlse[0]).abs().max().item() <= 1e-3, b
+
+
+def test_prefill_peer_output_single_rank():
+    """The fused-gather prefill entry with a world of one: same bits as the plain call, buffers alternate by step."""
+    torch.manual_seed(9)
+    B, Hq, Hkv, N, D = 2, 8, 2, 500, 128
+    q = torch.randn(B, Hq, N, D, device="cuda", dtype=torch.bfloat16)
+    k = torch.randn(B, Hkv, N, D, device="cuda", dtype=torch.bfloat16)
+    v = torch.randn(B, Hkv, N, D, device="cuda", dtype=torch.bfloat16)
+    ref, rlse = pli.flash_attention_forward(q, k, v, causal=True, return_lse=True)
+    po = pli.PeerOutput(B, Hq, D, torch.bfloat16, pli.make_shard(0, 1, Hq, Hkv, B), seq_len=N)
+    for step in range(3):
+        o, lse = pli.flash_attention_forward(q, k, v, causal=True, return_lse=True, peer_out=po)
+        assert torch.equal(o, ref) and torch.equal(lse, rlse), step
