@@ -80,7 +80,7 @@ struct PrefillParams {
     // per sequence (seq_lens[b]) and the mask is bottom-right aligned per sequence
     const int32_t* table;
     const int32_t* seq_lens;
-    int table_stride, page_size, layer, box_rows;
+    int table_stride, page_size, page_shift, layer, box_rows;       // page_size and box_rows are powers of two
     // ragged query lengths (paged kernels only): q / o are packed (total_q, Hq, D), rows [cu_q[b], cu_q[b+1]) belong
     // to sequence b; Nq is then the host's upper bound of the per-sequence lengths (it sizes the schedule)
     const int32_t* cu_q;
@@ -606,7 +606,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 kv_cnt += 2 * it.n_kv;
             }
-        } else if (warp == 14 && (kPaged || lane == 0)) {
+        } else if ((warp == 14 && (kPaged || lane == 0)) || (kPaged && warp == 15)) {
+            // paged K/V: two producer warps (14: Q and the K tiles, 15: the V tiles), every lane issuing one page box,
+            // because a tile is many small TMA operations there; otherwise one thread of warp 14 issues everything
+            const bool do_k = !kPaged || warp == 14, do_v = !kPaged || warp == 15;
             // =========================== TMA producer ===========================
             if (lane == 0) {
                 prefetch_tensormap(&map_q);
@@ -620,7 +623,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
                 auto load_q = [&](int t) {
-                    if (lane == 0) {
+                    if (lane == 0 && do_k) {
                         mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
                         mbar_arrive_expect_tx(&q_full[t], kTileBytes);
 #pragma unroll
@@ -638,17 +641,21 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 auto page_of = [&](int j) -> int {
                     if (!kPaged || lane >= n_boxes) return 0;
                     const int key = max(min(j * kBN + row0, it.nk - 1), 0);
-                    return p.table[(int64_t)it.b * p.table_stride + key / p.page_size];
+                    return p.table[(int64_t)it.b * p.table_stride + (key >> p.page_shift)];
                 };
-                auto load_kv = [&](const CUtensorMap* map, int j, int page) {
+                auto load_kv = [&](const CUtensorMap* map, int j, int page, bool mine) {
+                    if (!mine) {                          // the other producer warp's ring entry
+                        ++kv_cnt;
+                        return;
+                    }
                     const uint32_t slot = kv_cnt % kStages;
                     mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kStages) & 1) ^ 1);
                     if (lane == 0) mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
                     if constexpr (kPaged) {
                         __syncwarp();
                         if (lane < n_boxes) {
-                            const int in_page = max(min(j * kBN + row0, it.nk - 1), 0) % p.page_size;
-                            const int slot0 = in_page - in_page % p.box_rows;      // box-aligned slot inside the page
+                            const int in_page = max(min(j * kBN + row0, it.nk - 1), 0) & (p.page_size - 1);
+                            const int slot0 = in_page & ~(p.box_rows - 1);         // box-aligned slot inside the page
 #pragma unroll
                             for (int hf = 0; hf < kHalves; ++hf) {
                                 uint8_t* dst = sKV + slot * kTileBytes + hf * kSubTileBytes + row0 * 128;
@@ -674,15 +681,19 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     ++kv_cnt;
                 };
                 int page = page_of(0);
+                int page1 = page_of(it.n_kv > 1 ? 1 : 0);
                 load_q(0);
-                load_kv(&map_k, 0, page);
+                load_kv(&map_k, 0, page, do_k);
                 load_q(1);
-                load_kv(&map_v, 0, page);
+                load_kv(&map_v, 0, page, do_v);
                 for (int j = 1; j < it.n_kv; ++j) {
-                    page = page_of(j);
-                    load_kv(&map_k, j, page);
-                    load_kv(&map_v, j, page);
+                    // the table entry of tile j was requested one tile ago: its latency is not on the refill path
+                    const int next = page_of(j + 1 < it.n_kv ? j + 1 : j);
+                    load_kv(&map_k, j, page1, do_k);
+                    load_kv(&map_v, j, page1, do_v);
+                    page1 = next;
                 }
+
             }
         }
     }
@@ -888,7 +899,7 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
     p.debug_flags = g_debug_flags;
     p.table = nullptr;
     p.seq_lens = nullptr;
-    p.table_stride = p.page_size = p.layer = p.box_rows = 0;
+    p.table_stride = p.page_size = p.page_shift = p.layer = p.box_rows = 0;
     p.cu_q = nullptr;
     p.o_base = nullptr;
     p.o_st_tok = p.o_st_head = 0;
@@ -931,6 +942,7 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
     p.seq_lens = seq_lens;
     p.table_stride = table_stride;
     p.page_size = block_size;
+    p.page_shift = block_size == 16 ? 4 : block_size == 32 ? 5 : block_size == 64 ? 6 : 7;
     p.layer = layer;
     p.box_rows = box_rows;
     if (packed) {
