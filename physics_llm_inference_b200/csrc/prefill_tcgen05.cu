@@ -55,7 +55,7 @@ struct SmemLayout {
     static constexpr int kSumOff = kScaleOff + 4 * 128 * 4;        // float [2][128]
     static constexpr int kMaxOff = kSumOff + 2 * 128 * 4;          // float [2][128]
     static constexpr int kBarOff = kMaxOff + 2 * 128 * 4;
-    static constexpr int kNumBars = 4 + 2 * kKVStages + 22;
+    static constexpr int kNumBars = 4 + 4 * kKVStages + 22;       // the K/V ring has 2 x kKVStages half-size entries with pair MMAs
     static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kTmemPtrOff + 16;
 };
@@ -196,7 +196,15 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
 // of both CTAs have released it (tcgen05.commit multicast onto both CTAs' kv_empty barriers).
 // kPaged: K/V tiles are assembled from block-table pages (one TMA box per page / half page, issued by the lanes of
 // the producer warp) instead of one box per tile; everything downstream of shared memory is identical.
-template <int kD, bool kBf16, int kCluster, bool kPaged>
+// kPairMma (cluster of 2, contiguous K/V, D = 128): the pair's MMAs are CTA-pair instructions (tcgen05.mma.cta_group::2,
+// M = 256 = the 128 rows of tile t in each CTA), issued by the leader CTA (rank 0) for both.  Each CTA then holds only
+// HALF of every B operand in shared memory — for S = Q K^T the 32 keys [64 h + 32 rank, +32) of each 64-key half-step,
+// for O += P V the 64 head_dim columns [64 rank, +64) of all 128 keys — so the operand reads of the QK^T MMAs drop
+// from 6 KiB to 5 KiB per 32-cycle MMA slot (they are shared-memory-bandwidth bound: tools/probes/umma_rate.cu), the
+// K/V TMA writes into each CTA's shared memory halve, and no multicast is needed.  Barriers that gate the MMAs
+// (q_full, kv_full, pv_ok) live in the leader CTA and collect both CTAs' TMA bytes / arrivals; everything the MMAs
+// signal (s_full, kv_empty, q_empty, pv_tail, o_final) is committed to both CTAs.
+template <int kD, bool kBf16, int kCluster, bool kPaged, bool kPairMma = false>
 __global__ void __launch_bounds__(kThreads, 1)
 prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
@@ -205,8 +213,12 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     constexpr int kStages = L::kKVStages;
     constexpr int kTileBytes = L::kTileBytes;
     constexpr int kHalves = kD / 64;
-    constexpr uint32_t kIdescS = make_idesc_f16(kBM, kHN, kBf16, false, false);  // Q K^T (64 keys): both K-major
-    constexpr uint32_t kIdescO = make_idesc_f16(kBM, kD, kBf16, false, true);    // P V: B (V) is MN-major
+    static_assert(!kPairMma || (kCluster == 2 && !kPaged && kD == 128), "pair MMAs: cluster of 2, contiguous K/V, D = 128");
+    constexpr int kRing = kPairMma ? 2 * kStages : kStages;              // K/V ring entries ...
+    constexpr int kEntryBytes = kPairMma ? kTileBytes / 2 : kTileBytes;  // ... of this size (same total)
+    constexpr int kMmaM = kPairMma ? 2 * kBM : kBM;
+    constexpr uint32_t kIdescS = make_idesc_f16(kMmaM, kHN, kBf16, false, false);  // Q K^T (64 keys): both K-major
+    constexpr uint32_t kIdescO = make_idesc_f16(kMmaM, kD, kBf16, false, true);    // P V: B (V) is MN-major
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -219,11 +231,11 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* q_full = bars;                  // [2]      TMA -> MMA warp t
     uint64_t* q_empty = bars + 2;             // [2]      MMA warp t (commit) -> TMA
-    uint64_t* kv_full = bars + 4;             // [kStages] TMA -> both MMA warps
-    uint64_t* kv_empty = kv_full + kStages;   // [kStages] both MMA warps (commit, count 2) -> TMA
+    uint64_t* kv_full = bars + 4;             // [kRing] TMA -> both MMA warps
+    uint64_t* kv_empty = kv_full + kRing;     // [kRing] both MMA warps (commit, count 2) -> TMA
     // Index [t * 2 + h]: Q tile t, S/P buffer h (= half-step parity).  Each barrier has at most one phase
     // in flight, which is what lets S run two half-steps ahead of the softmax.
-    uint64_t* s_full = kv_empty + kStages;    // [4]  MMA (commit) -> softmax: S_t(s) is in buffer h
+    uint64_t* s_full = kv_empty + kRing;      // [4]  MMA (commit) -> softmax: S_t(s) is in buffer h
     // pv_ok: PV_t(s) may be issued: four softmax-warp arrivals (P_t(s) written over S in buffer h) + four
     // correction-warp arrivals (O_t rescaled for s >= 1; drained by the previous item / free at start for s == 0).
     uint64_t* pv_ok = s_full + 4;             // [4]
@@ -253,25 +265,38 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&pv_ok[i], 8);
+            mbar_init(&pv_ok[i], kPairMma ? 16 : 8);      // pair MMAs: both CTAs' warps arrive at the leader
             mbar_init(&sc_full[i], 4);
             mbar_init(&pv_tail[i], 1);        // [0..1] used
         }
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < kRing; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_empty[i], 2 * kCluster);    // both MMA warps of every CTA in the cluster
+            // both MMA warps of every CTA in the cluster; with pair MMAs only the leader's two issue (and commit to both)
+            mbar_init(&kv_empty[i], kPairMma ? 2 : 2 * kCluster);
         }
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(tmem_ptr, 512);
-        tmem_relinquish();
+        if constexpr (kPairMma) {
+            tmem_alloc_pair(tmem_ptr, 512);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
     if constexpr (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anything targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t cta_rank = kCluster > 1 ? cluster_ctarank() : 0;
+    // pv_ok of the CTA whose MMA warps wait on it (the pair's leader with pair MMAs, else this CTA); lane 0 of a warp
+    const uint32_t pv_ok_addr = kPairMma ? mapa_u32(smem_u32(pv_ok), 0) : smem_u32(pv_ok);
+    auto arrive_pv_ok = [&](int bi) {
+        if constexpr (kPairMma) mbar_arrive_cluster(pv_ok_addr + bi * 8);
+        else mbar_arrive(&pv_ok[bi]);
+    };
     // TMEM: S_t buffer h at column t*128 + h*64 (P aliases its first 32 columns); O_t at 256 + t*128.
 
     if (warp < 8) {
@@ -305,6 +330,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tmem_ld_x32(s_addr + 0, sv + 0);
                 tmem_ld_x32(s_addr + 32, sv + 32);
                 tc_wait_ld();
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 6, t, s);       // S in registers
                 // mask: key padding and the causal diagonal (warp-uniform test, per-row limit)
                 const int k0 = s * kHN;
                 const bool need_mask = (k0 + kHN > nk) || (p.causal && (k0 + kHN - 1 > q_tile0 + off));
@@ -336,6 +362,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sc_full[t * 2 + h]);
                 }
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 2, t, s);       // max known, scale factor posted
                 // P = exp2(S*c - m*c): packed FFMA2 for the argument, MUFU.EX2 (optionally an FMA-pipe polynomial
                 // for kPolyPairs of every 16 pairs), row sums in packed FADD2 chains.
                 const float2 c2 = make_float2(c, c);
@@ -361,10 +388,11 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 acc0 = fadd2(acc0, acc1);
                 d += acc0.x + acc0.y;
+                if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 7, t, s);       // exp2 / pack / TMEM stores issued
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&pv_ok[t * 2 + h]);
+                if (lane == 0) arrive_pv_ok(t * 2 + h);
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 3, t, s);       // P posted
             }
             mbar_wait(&stats_free[t], item_par ^ 1);      // previous item's epilogue has read the slots
@@ -386,8 +414,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         uint32_t sf_base = 0;                             // bit t*2+h: parity of s_full[t*2+h]'s first phase in this item
         if (lane == 0) {                                  // first item: O_0 / O_1 are free
-            mbar_arrive(&pv_ok[0]);
-            mbar_arrive(&pv_ok[2]);
+            arrive_pv_ok(0);
+            arrive_pv_ok(2);
         }
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, ++item_cnt) {
             const WorkItem it = decode_item(w, p);
@@ -423,7 +451,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         tc_fence_before();
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&pv_ok[bi]);
+                    if (lane == 0) arrive_pv_ok(bi);
                 }
             }
             // ---- epilogue: O_t / d -> bf16 -> swizzled smem -> TMA store; LSE ----
@@ -460,7 +488,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             tc_fence_before();
                             __syncwarp();
                             // O_t is in registers: the next item's PV_t(0) (buffer 0) may overwrite it
-                            if (lane == 0) mbar_arrive(&pv_ok[t * 2]);
+                            if (lane == 0) arrive_pv_ok(t * 2);
                         }
                         uint8_t* srow = sO + row * 128;
                         uint8_t* grow = nullptr;
@@ -506,8 +534,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (warp == 8 && lane == 0) tma_store_wait_all<0>();
     } else {
         reg_dealloc<64>();
-        if (warp == 12 || warp == 13) {
+        if ((warp == 12 || warp == 13) && !(kPairMma && cta_rank != 0)) {
             // =========================== MMA issuers: warp 12 -> Q tile 0, warp 13 -> Q tile 1 ===========================
+            // (pair MMAs: only in the leader CTA; tile t is then the 256 rows of both CTAs' Q tile t)
             // tcgen05.mma issue is nearly synchronous (the queue holds ~2 instructions), so each tile gets its own
             // issuing warp: while one waits on a barrier the other keeps the tensor pipe busy.  All 32 lanes run the
             // warp-uniform control flow (addresses stay in uniform registers); one elected lane issues.
@@ -523,39 +552,58 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const uint32_t tmem_s = tmem_base + t * 128, tmem_o = tmem_base + 256 + t * 128;
             uint32_t kv_cnt = 0, item_par = 0, pv_par = 0;        // pv_par bit h: phase parity of pv_ok[t*2+h]
             auto release_kv = [&](uint64_t* bar) {                // this Q tile is done with a ring slot
-                if constexpr (kCluster > 1) umma_commit_multicast(bar, (uint16_t)((1u << kCluster) - 1));
+                if constexpr (kPairMma) umma2_commit_multicast(bar, (uint16_t)3);
+                else if constexpr (kCluster > 1) umma_commit_multicast(bar, (uint16_t)((1u << kCluster) - 1));
+                else umma_commit(bar);
+            };
+            auto commit = [&](uint64_t* bar) {                    // to the waiters of this tile (in both CTAs of a pair)
+                if constexpr (kPairMma) umma2_commit_multicast(bar, (uint16_t)3);
                 else umma_commit(bar);
             };
             int trace_cur = 0;
             auto issue_S = [&](int s, uint32_t kslot) {
                 // S_t(s) = Q_t K[rows 64 (s&1) .. +64 of the tile]^T : K-major, 32 bytes of head_dim per MMA
-                const uint32_t ka = k_lo + kslot * (kTileBytes >> 4) + (s & 1) * ((kHN * 128) >> 4);
+                // (pair MMAs: this CTA's ring entry holds the half-step's 32 keys [64 h + 32 rank, +32) as rows
+                // [32 h, 32 h + 32) of two [64 rows][64 el] sub-tiles)
+                constexpr int kRowsS = kPairMma ? kHN / 2 : kHN;              // B rows per half-step in this CTA
+                constexpr int kSubK = kPairMma ? kSubTileBytes / 2 : kSubTileBytes;
+                const uint32_t ka = k_lo + kslot * (kEntryBytes >> 4) + (s & 1) * ((kRowsS * 128) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < kD / 16; ++ks) {
-                    const uint32_t koff = ((ks >> 2) * kSubTileBytes + (ks & 3) * 32) >> 4;
-                    umma_ss_lohi(tmem_s + (s & 1) * 64, q_lo + koff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
+                    const uint32_t qoff = ((ks >> 2) * kSubTileBytes + (ks & 3) * 32) >> 4;
+                    const uint32_t koff = ((ks >> 2) * kSubK + (ks & 3) * 32) >> 4;
+                    if constexpr (kPairMma)
+                        umma2_ss_lohi(tmem_s + (s & 1) * 64, q_lo + qoff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
+                    else
+                        umma_ss_lohi(tmem_s + (s & 1) * 64, q_lo + qoff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
                 }
             };
             auto issue_PV = [&](int s, uint32_t vslot) {
                 // O_t += P_t(s) V[rows 64 (s&1) .. +64] : A = P from TMEM (8 columns per 16 keys), B = V MN-major
-                const uint32_t va = v_lo + vslot * (kTileBytes >> 4) + (s & 1) * ((kHN * 128) >> 4);
+                // (pair MMAs: this CTA's ring entry holds head_dim columns [64 rank, +64) of all 128 keys: one sub-tile)
+                const uint32_t va = v_lo + vslot * (kEntryBytes >> 4) + (s & 1) * ((kHN * 128) >> 4);
 #pragma unroll
-                for (int ks = 0; ks < kHN / 16; ++ks)
-                    umma_ts_lohi(tmem_o, tmem_s + (s & 1) * 64 + ks * 8, va + ks * (2048 >> 4), kDescHi, kIdescO,
-                                 (s > 0 || ks > 0) ? 1u : 0u);
+                for (int ks = 0; ks < kHN / 16; ++ks) {
+                    if constexpr (kPairMma)
+                        umma2_ts_lohi(tmem_o, tmem_s + (s & 1) * 64 + ks * 8, va + ks * (2048 >> 4), kDescHi, kIdescO,
+                                      (s > 0 || ks > 0) ? 1u : 0u);
+                    else
+                        umma_ts_lohi(tmem_o, tmem_s + (s & 1) * 64 + ks * 8, va + ks * (2048 >> 4), kDescHi, kIdescO,
+                                     (s > 0 || ks > 0) ? 1u : 0u);
+                }
             };
             for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
                 const int nt = it.n[t];
-                auto slot_of = [&](uint32_t idx) -> uint32_t { return (kv_cnt + idx) % kStages; };
+                auto slot_of = [&](uint32_t idx) -> uint32_t { return (kv_cnt + idx) % kRing; };
                 auto wait_kv = [&](uint32_t idx) {
-                    mbar_wait(&kv_full[(kv_cnt + idx) % kStages], ((kv_cnt + idx) / kStages) & 1);
+                    mbar_wait(&kv_full[(kv_cnt + idx) % kRing], ((kv_cnt + idx) / kRing) & 1);
                 };
                 // K tile j is ring entry 2j, V tile j is ring entry 2j+1.  after_S(s): bookkeeping once S_t(s) is issued
                 auto after_S = [&](int s) {
-                    umma_commit(&s_full[t * 2 + (s & 1)]);
+                    commit(&s_full[t * 2 + (s & 1)]);
                     if ((s & 1) || s == nt - 1) release_kv(&kv_empty[slot_of(2 * (s >> 1))]);   // K tile done (this Q tile)
-                    if (s == nt - 1) umma_commit(&q_empty[t]);
+                    if (s == nt - 1) commit(&q_empty[t]);
                 };
                 // ---- prologue: S_t(0), S_t(1) from K tile 0 ----
                 mbar_wait(&q_full[t], item_par);
@@ -581,8 +629,8 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     trace_event(p, lane, 2 + t, trace_cur, 4, t, s);                        // inputs of PV_t(s) ready
                     if (elect_one()) {
                         issue_PV(s, slot_of(2 * (s >> 1) + 1));
-                        if (s + 2 == nt || nt == 1) umma_commit(&pv_tail[t]);           // no S follows this PV
-                        if (s == nt - 1) umma_commit(&o_final[t]);
+                        if (s + 2 == nt || nt == 1) commit(&pv_tail[t]);                // no S follows this PV
+                        if (s == nt - 1) commit(&o_final[t]);
                         if (h || s == nt - 1) release_kv(&kv_empty[slot_of(2 * (s >> 1) + 1)]);   // V tile done (this Q tile)
                         if (more) {
                             issue_S(s + 2, slot_of(2 * ((s + 2) >> 1)));
@@ -618,18 +666,29 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 prefetch_tensormap(&map_o);
             }
             uint32_t kv_cnt = 0, item_par = 0;
-            const int rank = kCluster > 1 ? (int)cluster_ctarank() : 0;
+            const int rank = (int)cta_rank;
+            const uint32_t q_full_leader = kPairMma ? mapa_u32(smem_u32(q_full), 0) : 0;
+            const uint32_t kv_full_leader = kPairMma ? mapa_u32(smem_u32(kv_full), 0) : 0;
             const uint16_t cmask = (uint16_t)((1u << kCluster) - 1);
             for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
                 const WorkItem it = decode_item(w, p);
                 auto load_q = [&](int t) {
                     if (lane == 0 && do_k) {
                         mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
-                        mbar_arrive_expect_tx(&q_full[t], kTileBytes);
+                        if constexpr (kPairMma) {
+                            // both CTAs' Q tiles are counted by the leader's barrier (its MMA warp issues for the pair)
+                            if (rank == 0) mbar_arrive_expect_tx(&q_full[t], 2 * kTileBytes);
 #pragma unroll
-                        for (int hf = 0; hf < kHalves; ++hf)
-                            tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
-                                        it.qbase + it.q0[t], it.h[t], it.bq);
+                            for (int hf = 0; hf < kHalves; ++hf)
+                                tma_load_4d_pair(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, q_full_leader + t * 8,
+                                                 hf * 64, it.qbase + it.q0[t], it.h[t], it.bq);
+                        } else {
+                            mbar_arrive_expect_tx(&q_full[t], kTileBytes);
+#pragma unroll
+                            for (int hf = 0; hf < kHalves; ++hf)
+                                tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
+                                            it.qbase + it.q0[t], it.h[t], it.bq);
+                        }
                     }
                 };
                 // paged: this lane's box of every K/V tile covers tile rows [row0, row0 + box_rows); its page id is
@@ -648,8 +707,28 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         ++kv_cnt;
                         return;
                     }
-                    const uint32_t slot = kv_cnt % kStages;
-                    mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kStages) & 1) ^ 1);
+                    const uint32_t slot = kv_cnt % kRing;
+                    mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kRing) & 1) ^ 1);
+                    if constexpr (kPairMma) {
+                        // this CTA's half of the B operand, reported to the leader's barrier (lane 0 only runs this):
+                        // K: keys [64 h + 32 rank, +32) of both half-steps h (map_k carries 32-row boxes);
+                        // V: head_dim columns [64 rank, +64) of all 128 keys (map_v carries 128-row boxes)
+                        if (rank == 0) mbar_arrive_expect_tx(&kv_full[slot], 2 * kEntryBytes);
+                        uint8_t* dst = sKV + slot * kEntryBytes;
+                        const uint32_t bar = kv_full_leader + slot * 8;
+                        if (map == &map_k) {
+#pragma unroll
+                            for (int hf = 0; hf < kHalves; ++hf)
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh)
+                                    tma_load_4d_pair(dst + hf * (kSubTileBytes / 2) + hh * (32 * 128), map, bar, hf * 64,
+                                                     j * kBN + hh * kHN + rank * 32, it.hk, it.b);
+                        } else {
+                            tma_load_4d_pair(dst, map, bar, rank * 64, j * kBN, it.hk, it.b);
+                        }
+                        ++kv_cnt;
+                        return;
+                    }
                     if (lane == 0) mbar_arrive_expect_tx(&kv_full[slot], kTileBytes);
                     if constexpr (kPaged) {
                         __syncwarp();
@@ -702,7 +781,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     tc_fence_before();
     __syncthreads();
     if constexpr (kCluster > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
-    if (warp == 0) tmem_dealloc(tmem_base, 512);
+    if (warp == 0) {
+        if constexpr (kPairMma) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -801,6 +883,17 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// CTA-pair MMAs are opt-in (PLI_PAIR_MMA=1 in the environment, or bit 1 of pli_debug_prefill_trace's flags): measured
+// equal to per-CTA MMAs + TMA multicast on the whole chip (1287-1292 vs 1288-1294 TFLOP/s on C2) and 2.5 % slower per SM
+// on part of it, so the simpler protocol stays the default.
+bool pair_mma_env() {
+    static const bool on = [] {
+        const char* e = getenv("PLI_PAIR_MMA");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 // PLI_NO_CLUSTER=1 in the environment forces the single-CTA kernel (A/B measurements)
 bool cluster_mode_enabled() {
     static const bool on = [] {
@@ -840,14 +933,19 @@ const PeerMaps& no_peers() {
     return none;
 }
 
-template <int kD, bool kBf16, int kCluster, bool kPaged = false>
+template <int kD, bool kBf16, int kCluster, bool kPaged = false, bool kPairMma = false>
 int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
              const PrefillParams& p, cudaStream_t stream, const PeerMaps& peers = no_peers()) {
-    auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster, kPaged>;
+    auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster, kPaged, kPairMma>;
     const int smem = SmemLayout<kD>::kTotal + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
     int grid = sm_count();
     if (grid <= 0) grid = 148;
+    static const int max_ctas = [] {                    // PLI_MAX_CTAS: tuning experiments on a part of the chip
+        const char* e = getenv("PLI_MAX_CTAS");
+        return e ? atoi(e) : 0;
+    }();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     if (grid > p.total_items) grid = p.total_items;
     if (kCluster > 1) grid -= grid % kCluster;          // total_items is a multiple of kCluster in this mode
     cudaLaunchConfig_t cfg = {};
@@ -990,8 +1088,10 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     // (even, odd) items share their K/V when the per-group item count is even: group size divisible by 4 with
     // head-pair items (group size odd -> row-pair items of single heads -> never)
     const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
-    if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pairs ? kHN : kBN))) return rc;
-    if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pairs ? kHN : kBN))) return rc;
+    // pair MMAs (D = 128): each CTA loads 32-key boxes of K and full-height, 64-column boxes of V (its half of B)
+    const bool pair_mma = pairs && D == 128 && (pair_mma_env() || (g_debug_flags & 2));
+    if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pair_mma ? kHN / 2 : pairs ? kHN : kBN))) return rc;
+    if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pair_mma ? kBN : pairs ? kHN : kBN))) return rc;
     if (peer != nullptr) mo = pm.maps[0][0];
     else if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
     PrefillParams p;
@@ -1010,6 +1110,10 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
 #define PLI_GO(DD, BF)                                                                            \
     return pairs ? launch_t<DD, BF, 2>(mq, mk, mv, mo, p, stream, pm) : launch_t<DD, BF, 1>(mq, mk, mv, mo, p, stream, pm)
     if (D == 128) {
+        if (pair_mma) {
+            if (bf16) return launch_t<128, true, 2, false, true>(mq, mk, mv, mo, p, stream, pm);
+            return launch_t<128, false, 2, false, true>(mq, mk, mv, mo, p, stream, pm);
+        }
         if (bf16) PLI_GO(128, true);
         PLI_GO(128, false);
     }
@@ -1023,7 +1127,8 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
 using namespace pli;
 
 // Debug aid: record CTA 0's pipeline timeline of the next prefill launches into `buf` (device memory of
-// 3 regions x capacity x 16 bytes, zeroed by the caller); buf = NULL switches it off.  flags bit 0 skips exp2.
+// 4 regions x capacity x 16 bytes, zeroed by the caller); buf = NULL switches it off.  flags bit 1: CTA-pair MMAs
+// (tcgen05.mma.cta_group::2) for the following launches (tuning / tests).
 extern "C" int pli_debug_prefill_trace(void* buf, int capacity, int flags) {
     g_trace_buf = static_cast<unsigned long long*>(buf);
     g_trace_cap = buf ? capacity : 0;

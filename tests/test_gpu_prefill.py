@@ -220,6 +220,39 @@ def test_prefill_is_deterministic_and_race_free(shape, causal):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,causal", [
+    ((2, 8, 2, 1024, 1024, 128), True),      # C2 scaled down: two CTA pairs per KV group and row block
+    ((1, 4, 1, 300, 300, 128), True),        # ragged last tile, a single pair
+    ((2, 16, 2, 384, 1000, 128), True),      # chunk over cache (offset mask), group size 8
+    ((4, 32, 8, 256, 256, 128), False),      # more pairs than the chip has SM pairs
+    ((1, 8, 2, 2048, 2048, 128), True),      # lazy rescales across many steps (inputs below)
+])
+def test_pair_mma_variant_matches_default_bitwise(shape, causal, dtype):
+    """The opt-in CTA-pair MMA kernel (tcgen05.mma.cta_group::2: M = 256 across the two CTAs of a cluster, each CTA
+    holding half of K / V in shared memory, barriers collected in the leader CTA) does the same arithmetic in the same
+    order as the default kernel: outputs must be bit-identical, run after run, and within tolerance of the oracle."""
+    from physics_llm_inference_b200 import _lib
+    lib = _lib.load()
+    B, Hq, Hkv, Nq, Nk, D = shape
+    q, k, v = orc.seeded_qkv(91, B, Hq, Hkv, Nq, Nk, D)
+    k = k * torch.linspace(0.5, 4.0, Nk).view(1, 1, Nk, 1)
+    qd, kd, vd = q.to(dtype).cuda(), k.to(dtype).cuda(), v.to(dtype).cuda()
+    o0, l0 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
+    torch.cuda.synchronize()
+    try:
+        _lib.check(lib.pli_debug_prefill_trace(None, 0, 2))          # flags bit 1: pair MMAs for the next launches
+        for _ in range(5):
+            o1, l1 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
+            torch.cuda.synchronize()
+            assert torch.equal(o1, o0) and torch.equal(l1, l0)
+    finally:
+        _lib.check(lib.pli_debug_prefill_trace(None, 0, 0))
+    ro, rl = orc.flash_attention_oracle(qd, kd, vd, causal=causal)
+    assert (o1.float().cpu() - ro).abs().max().item() <= 2e-2
+    assert (l1.cpu() - rl).abs().max().item() <= 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("bs,D,Hkv,G,Nq,lens", [
     (16, 128, 2, 4, 128, [512, 300, 128]),          # C3-style pages, cluster pairs (G % 4 == 0), ragged cache lengths
     (16, 128, 1, 2, 200, [777, 200]),               # head pairs without cluster, ragged Nq tile

@@ -17,17 +17,29 @@ cap = 20000
 buf = torch.zeros(4 * cap * 2, dtype=torch.int64, device="cuda")
 lib.pli_debug_prefill_trace(buf.data_ptr(), cap, flags)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+# argv[2] = number of untraced launches issued back to back in front of the traced one (the traced launch then
+# runs under the clocks / power state of a burst of that length)
+lead = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+if lead:
+    lib.pli_debug_prefill_trace(None, 0, 0)
+    for _ in range(lead):
+        pli.flash_attention_forward(q, k, v, causal=True)
+    lib.pli_debug_prefill_trace(buf.data_ptr(), cap, flags)
 e0.record()
 pli.flash_attention_forward(q, k, v, causal=True)
 e1.record()
 torch.cuda.synchronize()
 lib.pli_debug_prefill_trace(None, 0, 0)
-print(f"flags={flags} kernel {e0.elapsed_time(e1):.3f} ms (with tracing)")
+ms = e0.elapsed_time(e1)
+print(f"flags={flags} kernel {ms:.3f} ms (with tracing), after {lead} back-to-back launches")
 h = buf.cpu().tolist()
 recs = [(h[2 * i + 1], h[2 * i] & 0xFF, (h[2 * i] >> 8) & 0xFF, (h[2 * i] >> 16) & 0xFFFF) for i in range(4 * cap) if h[2 * i] >> 40]
 recs.sort()
 t0 = recs[0][0]
-names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "mma: V landed", 7: "mma: O corrected", 8: "mma: P seen"}
+span = recs[-1][0] - t0
+print(f"CTA 0: {span} SM cycles between its first and last event = {span / ms / 1e3:.0f} MHz if they span the kernel "
+      f"(the SM clock the kernel actually ran at; nvidia-smi's samples are too coarse to see it)")
+names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "S_in_registers", 7: "exp_done"}
 print("first item: events of half-steps 40..44 (regions: softmax tile 0/1, MMA warp of tile 0/1)")
 for clk, ev, t, j in recs:
     if 40 <= j <= 44 and clk - t0 < 800000:
@@ -49,6 +61,11 @@ for t in (0, 1):
     js = sorted(j for (tt, j) in ev if tt == t and 10 <= j <= 110)
     soft = [ev[(t, j)][3] - ev[(t, j)][1] for j in js if 3 in ev[(t, j)] and 1 in ev[(t, j)]]
     mx = [ev[(t, j)][2] - ev[(t, j)][1] for j in js if 2 in ev[(t, j)] and 1 in ev[(t, j)]]
+    ld = [ev[(t, j)][6] - ev[(t, j)][1] for j in js if 6 in ev[(t, j)] and 1 in ev[(t, j)]]
+    ex = [ev[(t, j)][7] - ev[(t, j)][2] for j in js if 7 in ev[(t, j)] and 2 in ev[(t, j)]]
+    tail = [ev[(t, j)][3] - ev[(t, j)][7] for j in js if 7 in ev[(t, j)] and 3 in ev[(t, j)]]
+    print(f"tile{t}: softmax phases: TMEM load {avg(ld):.0f} | max + scale post {avg(mx) - avg(ld):.0f} | exp2/pack/store issue {avg(ex):.0f} | "
+          f"wait::st + fence + arrive {avg(tail):.0f}")
     p2go = [ev[(t, j)][4] - ev[(t, j)][3] for j in js if 4 in ev[(t, j)] and 3 in ev[(t, j)]]
     issue = [ev[(t, j)][5] - ev[(t, j)][4] for j in js if 5 in ev[(t, j)] and 4 in ev[(t, j)]]
     turn = [ev[(t, j + 1)][1] - ev[(t, j)][5] for j in js if (t, j + 1) in ev and 1 in ev[(t, j + 1)] and 5 in ev[(t, j)]]
