@@ -563,11 +563,17 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (seeded N(0,1), random-init)", "config": config_dict(world),
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms, "steps": e2e_steps,
+        # both drivings are full end-to-end steps through the public call; the headline is the faster one on this box
+        # (on some hosts the two PCIe directions do not overlap and the single-stream order wins)
+        "e2e": {"value": max(e2e_val, flops_step * world / (e2e_serial_ms * 1e-3) / 1e12), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": min(e2e_ms, e2e_serial_ms), "steps": e2e_steps,
+                "driving": "pipelined" if e2e_ms <= e2e_serial_ms else "serial",
+                "pipelined_value": e2e_val, "pipelined_ms_per_step": e2e_ms,
                 "serial_value": flops_step * world / (e2e_serial_ms * 1e-3) / 1e12, "serial_ms_per_step": e2e_serial_ms,
                 "note": "every step: q,k,v copied from pinned host memory, flash_attention_forward, O copied back; "
-                        "value = steps pipelined over three streams (double-buffered), serial_value = one stream"},
+                        "pipelined = steps over three streams (double-buffered), serial = one stream; "
+                        "value = the faster of the two on this box"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": value / world, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": value / world / peaks["bf16_tflops"],

@@ -1,4 +1,4 @@
-"""Short, fixed workloads for ncu captures (one GPU): `python tools/profile_target.py prefill|decode [reps]`."""
+"""Short, fixed workloads for ncu captures (one GPU): `python tools/profile_target.py prefill|paged|decode [reps]`."""
 import os
 import sys
 
@@ -17,6 +17,17 @@ if which == "prefill":
     v = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
     for _ in range(reps):
         pli.flash_attention_forward(q, k, v, causal=True)
+elif which == "paged":
+    # C2 read in place from 16-token pages (chunk = whole prompt): the kPaged instance of the prefill kernel
+    B, Hq, Hkv, N, D, bs = 4, 32, 8, 8192, 128, 16
+    P = B * N // bs
+    kp = torch.randn(P, 1, bs, Hkv, D, device="cuda").bfloat16()
+    vp = torch.randn(P, 1, bs, Hkv, D, device="cuda").bfloat16()
+    table = torch.randperm(P).to(torch.int32).view(B, N // bs).cuda()
+    lens = torch.full((B,), N, dtype=torch.int32, device="cuda")
+    q = torch.randn(B, Hq, N, D, device="cuda").bfloat16()
+    for _ in range(reps):
+        pli.flash_attention_paged(q, kp, vp, table, lens, max_seq_len=N)
 else:
     B, Hq, Hkv, D, L, bs = 64, 32, 8, 128, 4096, 16
     P = B * L // bs
