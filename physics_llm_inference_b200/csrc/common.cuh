@@ -434,6 +434,10 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, bool bf16, b
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // ---- register budget per warp role -----------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void reg_alloc() {

@@ -12,6 +12,7 @@
 //                       with TMA (one box per page, page ids from the block table), four consumer
 //                       warps run QK^T and PV on mma.sync m16n8k16 via ldmatrix, fp32 softmax state.
 //   decode_simt_kernel  everything else (f32 storage, odd head_dim / page size): CUDA cores.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -229,6 +230,10 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         fence_barrier_init();
     }
     __syncthreads();
+    // programmatic dependent launch: the combine pass (launched with programmatic stream serialisation) may be
+    // scheduled as soon as every CTA of this grid is running; it still waits for this grid's completion and memory
+    // flush in its own griddepcontrol.wait, so only its launch latency is hidden.  No-op without a dependent.
+    pdl_launch_dependents();
 
     if (warp == kConsumerWarps) {
         // ===================== producer warp: TMA page loads =====================
@@ -455,6 +460,7 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __rest
                                                              int64_t osb, int64_t osh, const PeerScatter peer) {
     const int h = blockIdx.x, b = blockIdx.y;
     const int64_t row = ((int64_t)b * Hq + h) * S;
+    pdl_wait();                     // the split-KV grid before this one has completed and its partials are visible
     float M = -INFINITY;
     for (int s = 0; s < S; ++s) M = fmaxf(M, lse_part[row + s]);
     float den = 0.f;
@@ -747,6 +753,15 @@ extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void
                         static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr);
 }
 
+// PLI_NO_PDL=1 in the environment launches the combine pass as a plain stream-ordered kernel (A/B measurements)
+static bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PLI_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 static int combine_impl(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
                         const int64_t o_strides[2], int dtype, void* stream_, const PeerScatter& peer) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -755,14 +770,25 @@ static int combine_impl(const void* workspace, void* o, float* lse, int B, int H
     if (B > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B > 65535");
     const float* o_part = static_cast<const float*>(workspace);
     const float* lse_part = o_part + (size_t)B * Hq * num_splits * D;
-    dim3 grid(Hq, B);
     const int threads = D >= 128 ? 128 : (D >= 64 ? 64 : 32);
+    // programmatic dependent launch behind the split-KV kernel on the same stream (the kernel waits in pdl_wait())
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Hq, B);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int64_t osb = o_strides[0], osh = o_strides[1];
     if (dtype == PLI_F32)
-        decode_combine_kernel<float><<<grid, threads, 0, stream>>>(o_part, lse_part, (float*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1], peer);
+        PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_combine_kernel<float>, o_part, lse_part, (float*)o, lse, Hq, D, num_splits, osb, osh, peer));
     else if (dtype == PLI_BF16)
-        decode_combine_kernel<__nv_bfloat16><<<grid, threads, 0, stream>>>(o_part, lse_part, (__nv_bfloat16*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1], peer);
+        PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_combine_kernel<__nv_bfloat16>, o_part, lse_part, (__nv_bfloat16*)o, lse, Hq, D, num_splits, osb, osh, peer));
     else if (dtype == PLI_F16)
-        decode_combine_kernel<__half><<<grid, threads, 0, stream>>>(o_part, lse_part, (__half*)o, lse, Hq, D, num_splits, o_strides[0], o_strides[1], peer);
+        PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_combine_kernel<__half>, o_part, lse_part, (__half*)o, lse, Hq, D, num_splits, osb, osh, peer));
     else
         return set_error(PLI_ERR_INVALID, "unknown dtype %d", dtype);
     PLI_CUDA_CHECK(cudaGetLastError());
