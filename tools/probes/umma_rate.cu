@@ -163,6 +163,46 @@ __global__ void __launch_bounds__(320, 1) umma_rate_kernel(int mode, int reps, i
             out->cycles = t1 - t0;
             out->reps = reps;
         }
+    } else if (warp >= 2 && noise >= 3) {
+        // softmax-like ALU work from 8 warps (two per scheduler), no memory traffic at all: per 64 "elements" 32 packed
+        // FMAs, 48 MUFU.EX2, 32 packed adds, 32 bf16x2 packs; noise 4 adds the TMEM loads / stores of noise 2
+        const int t = (warp - 2) >> 2;
+        const uint32_t lane_addr = (uint32_t)(((warp - 2) & 3) * 32) << 16;
+        float2 acc = make_float2(0.f, 0.f);
+        uint32_t sink = 0;
+        float seed = 1e-3f * (float)threadIdx.x;
+        while (!*stop) {
+            uint32_t a[32], b[32];
+            if (noise == 4) {
+                tmem_ld_x32(tmem_base + t * 128 + lane_addr, a);
+                tmem_ld_x32(tmem_base + t * 128 + 32 + lane_addr, b);
+                tc_wait_ld();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { a[i] = __float_as_uint(seed + i); b[i] = __float_as_uint(seed - i); }
+            }
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float2 x = ffma2(make_float2(__uint_as_float(a[i]) * 1e-30f, __uint_as_float(b[i]) * 1e-30f),
+                                 make_float2(0.5f, 0.5f), make_float2(-1.f, -1.f));
+                float2 e;
+                if (i < 8) e = exp2_poly2(x);
+                else { e.x = ex2_approx(x.x); e.y = ex2_approx(x.y); }
+                acc = fadd2(acc, e);
+                pk[i] = pack2<true>(e.x, e.y);
+            }
+            if (noise == 4) {
+                tmem_st_x16(tmem_base + t * 128 + 64 + lane_addr, pk);
+                tmem_st_x16(tmem_base + t * 128 + 80 + lane_addr, pk + 16);
+                tc_wait_st();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sink ^= pk[i];
+            }
+            seed += acc.x * 1e-30f;
+        }
+        if (sink == 0x12345678u || acc.y == 123.f) out->reps = -1;
     } else if (warp >= 2 && noise) {
         // softmax-like TMEM traffic from 8 warps (two per lane quarter): read 64 columns, write 32
         const int t = (warp - 2) >> 2;
@@ -301,8 +341,9 @@ int main(int argc, char** argv) {
                            "kernel pair + commits where the kernel has them",
                            "kernel pair + 3 commits behind each batch",
                            "kernel pair + 1 commit behind each batch"};
-    for (int noise = 0; noise <= 2; noise += 2) {
-        printf("--- TMEM noise level %d (0 none, 1 loads, 2 loads + stores) ---\n", noise);
+    for (int noise = 0; noise <= 4; ++noise) {
+        if (noise == 1) continue;
+        printf("--- noise level %d (0 none, 2 TMEM loads + stores, 3 softmax-like ALU work, 4 both) ---\n", noise);
         for (int mode = 0; mode < 12; ++mode) {
             for (int warm = 0; warm < 2; ++warm) {
                 umma_rate_kernel<<<148, 320, kSmem>>>(mode, reps, noise, d);
