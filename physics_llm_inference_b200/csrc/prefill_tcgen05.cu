@@ -787,6 +787,533 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
 }
 
+// ================================================================================================
+// prefill_wide_kernel (D = 128, CTA pairs, contiguous K/V): ONE 128-row Q tile per CTA, S tiles 128 keys wide in THREE
+// TMEM buffers, CTA-pair MMAs.
+//
+// Why: with two Q tiles per CTA the S buffers can only be 64 keys wide (2 x (2 x 64 + 128 O) = 512 TMEM columns), and a
+// Q K^T MMA of N = 64 re-reads its A operand for every 64 keys: 6 KiB of shared memory per 32-cycle slot against a
+// 128 B/clk port (1283 instead of 1024 cycles per 8.4 MFLOP).  One Q tile leaves room for three 128-key
+// S buffers (3 x 128 + 128 O = 512): S MMAs run at N = 128 (at the tensor floor), S runs up to two 128-key steps ahead
+// of the softmax, and the pair's MMAs (M = 256: this CTA's q head and its neighbour's, which share the KV head) halve
+// the B-operand bytes each CTA holds and reads.
+//
+//   warps 0-7   softmax: warpgroup (w >> 2) takes every other 128-key step, one thread per row (see below)
+//   warps 8-11  correction (lazy O rescale) + epilogue, as in prefill_tcgen05_kernel
+//   warp 12     MMA issuer (leader CTA only)      warp 14  TMA producer (each CTA: its Q tile and its half of K / V)
+//
+// TMEM: S/P buffer b at column 128 b (P(j) = bf16 of 128 keys in its LAST 64 columns), O at 384.
+// ================================================================================================
+struct WideLayout {
+    static constexpr int kTileBytes = 2 * kSubTileBytes;       // Q tile [128 x 128]
+    static constexpr int kEntryBytes = kTileBytes / 2;         // this CTA's half of a K or V tile
+    static constexpr int kRing = 8;
+    static constexpr int kQOff = 0;
+    static constexpr int kKVOff = kTileBytes;
+    static constexpr int kOOff = kKVOff + kRing * kEntryBytes;   // one [128 x 64] staging sub-tile
+    static constexpr int kScaleOff = kOOff + kSubTileBytes;      // float [3][128]
+    static constexpr int kMrefOff = kScaleOff + 3 * 128 * 4;     // float [3][128]: reference maximum after step j (slot j % 3)
+    static constexpr int kSumOff = kMrefOff + 3 * 128 * 4;       // float [<= 3 warpgroups][128]
+    static constexpr int kMaxOff = kSumOff + 3 * 128 * 4;        // float [<= 3 warpgroups][128]
+    static constexpr int kBarOff = kMaxOff + 3 * 128 * 4;
+    static constexpr int kNumBars = 2 + 2 * kRing + 3 + 3 + 3 + 3 + 3 + 3;
+    static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
+    static constexpr int kTotal = kTmemPtrOff + 16;
+};
+
+struct WideItem {
+    int b, hk, h, q0, n, nk, nq;      // batch, kv head, q head, first row, 128-key steps, keys, query rows
+};
+
+// Same block order as decode_item (blocks of pair_block 128-row slots, longest first, KV-group-major inside a block);
+// consecutive items (2k, 2k + 1) are q heads (2i, 2i + 1) of one KV group at the same rows: the two CTAs of a pair.
+__device__ __forceinline__ WideItem decode_wide(int w, const PrefillParams& p) {
+    WideItem it;
+    const int G = p.Hq / p.Hkv;
+    const int per_slot = p.B * p.Hkv * G;
+    const int kPB = p.pair_block;
+    const int blk = w / (kPB * per_slot);
+    int r = w - blk * kPB * per_slot;
+    const int top = p.num_pairs - 1 - blk * kPB;
+    const int cnt = min(kPB, top + 1);
+    const int g = r / (cnt * G);
+    r -= g * cnt * G;
+    const int slot = top - r / G;
+    it.b = g / p.Hkv;
+    it.hk = g % p.Hkv;
+    it.h = it.hk * G + r % G;
+    it.q0 = slot * kBM;
+    it.nk = p.Nk;
+    it.nq = p.Nq;
+    int kmax = it.nk;
+    if (p.causal) kmax = min(it.nk, it.q0 + kBM + (it.nk - it.nq));
+    kmax = max(kmax, 1);
+    it.n = (kmax + kBN - 1) / kBN;
+    return it;
+}
+
+// kGroups softmax warpgroups (2: 512 threads; 3: 576 threads, one warpgroup per S buffer, 112 registers per thread)
+template <int kGroups>
+struct WideRoles {
+    static constexpr int kSoftWarps = 4 * kGroups;
+    static constexpr int kCorrWarp0 = kSoftWarps;          // four correction / epilogue warps
+    static constexpr int kMmaWarp = kSoftWarps + 4;
+    static constexpr int kTmaWarp = kSoftWarps + 5;
+    static constexpr int kThreadsWide = kGroups == 2 ? 512 : (kSoftWarps + 6) * 32;
+};
+
+template <bool kBf16, int kGroups>
+__global__ void __launch_bounds__(WideRoles<kGroups>::kThreadsWide, 1)
+prefill_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_o,
+                    const PrefillParams p, const __grid_constant__ PeerMaps peers) {
+    using L = WideLayout;
+    using R = WideRoles<kGroups>;
+    constexpr int kD = 128;
+    constexpr int kRing = L::kRing;
+    constexpr int kEntryBytes = L::kEntryBytes;
+    constexpr int kTileBytes = L::kTileBytes;
+    constexpr uint32_t kIdescS = make_idesc_f16(2 * kBM, kBN, kBf16, false, false);   // Q K^T, 128 keys
+    constexpr uint32_t kIdescO = make_idesc_f16(2 * kBM, kD, kBf16, false, true);     // P V
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem + L::kQOff;
+    uint8_t* sKV = smem + L::kKVOff;
+    uint8_t* sO = smem + L::kOOff;
+    float* sScale = reinterpret_cast<float*>(smem + L::kScaleOff);   // [3][128]
+    float* sMref = reinterpret_cast<float*>(smem + L::kMrefOff);     // [3][128]
+    float* sSum = reinterpret_cast<float*>(smem + L::kSumOff);       // [2][128]
+    float* sMax = reinterpret_cast<float*>(smem + L::kMaxOff);       // [2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+    uint64_t* q_full = bars;                   // leader: both CTAs' Q tiles (TMA bytes)
+    uint64_t* q_empty = bars + 1;              // MMA commit (both CTAs) -> TMA
+    uint64_t* kv_full = bars + 2;              // [kRing] leader: both CTAs' halves
+    uint64_t* kv_empty = kv_full + kRing;      // [kRing] MMA commit (both CTAs) -> TMA
+    uint64_t* s_full = kv_empty + kRing;       // [3] MMA commit (both CTAs) -> softmax: S(j) is in buffer j % 3
+    uint64_t* pv_ok = s_full + 3;              // [3] leader: 2 x (4 softmax warps "P written" + 4 correction warps "O ready")
+    uint64_t* sc_full = pv_ok + 3;             // [3] softmax (4 warps) -> correction: scale factor of step j
+    uint64_t* mref_full = sc_full + 3;         // [3] softmax (4 warps) -> the other warpgroup: reference maximum after step j
+    uint64_t* pv_done = mref_full + 3;         // [3] MMA commit (both CTAs) after PV(j), slot j % 3 -> correction (waited on when rescaling)
+    uint64_t* o_final = pv_done + 3;           // MMA commit (both CTAs) after the last PV of an item -> epilogue
+    uint64_t* stats_full = o_final + 1;        // softmax (8 warps) -> epilogue
+    uint64_t* stats_free = stats_full + 1;     // epilogue (4 warps) -> softmax
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
+        for (int i = 0; i < kRing; ++i) {
+            mbar_init(&kv_full[i], 1);
+            mbar_init(&kv_empty[i], 1);
+        }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&pv_ok[i], 16);
+            mbar_init(&sc_full[i], 4);
+            mbar_init(&mref_full[i], 4);
+        }
+        for (int i = 0; i < 3; ++i) mbar_init(&pv_done[i], 1);
+        mbar_init(o_final, 1);
+        mbar_init(stats_full, R::kSoftWarps);
+        mbar_init(stats_free, 4);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc_pair(tmem_ptr, 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t cta_rank = cluster_ctarank();
+    const uint32_t pv_ok_leader = mapa_u32(smem_u32(pv_ok), 0);
+    const uint32_t tmem_o = tmem_base + 384;
+
+    if (warp < R::kSoftWarps) {
+        // =========================== softmax ===========================
+        // Warpgroup g = warp >> 2 takes the 128-key steps j = g, g + kGroups, ...: one thread per row, the whole row of a step.
+        // A row of 128 scores does not fit in registers next to its P, so the thread walks it in two 64-key halves:
+        // load half 0 -> max, load half 1 -> max, (row max known) exp2 half 1 -> P, reload half 0 -> exp2 -> P.
+        // P(j) goes into columns [64, 128) of its S buffer, so the reload of half 0 (columns [0, 64)) still sees S.
+        // The two warpgroups run one step apart, so a step may take two MMA periods; the running reference maximum
+        // of a row is handed from step to step through shared memory (sMref, mref_full).
+        if constexpr (kGroups == 2) reg_alloc<176>();
+        const int g = warp >> 2;
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(qd * 32) << 16;
+        const float cs = p.scale_log2;
+        uint32_t ph_base = 0;                              // bit b: parity of the phases buffer b completed in earlier items
+        for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd) {
+            const uint32_t item_par = rnd & 1;
+            const WideItem it = decode_wide(w, p);
+            const int q_row = it.q0 + row;
+            const int nk = it.nk, off = it.nk - it.nq;
+            float m_own = -INFINITY, d = 0.f;              // this thread's reference maximum and partial row sum
+            for (int j = g; j < it.n; j += kGroups) {
+                const int b = j % 3;
+                const uint32_t par = ((ph_base >> b) ^ (uint32_t)(j / 3)) & 1u;
+                const uint32_t s_addr = tmem_base + b * 128 + lane_addr;
+                // A warpgroup waits on every other phase of a barrier, and a parity wait is only meaningful while the
+                // barrier is at most one phase behind: S(j-1) complete (MMAs complete in order) implies that the phase
+                // before the one waited for has completed on every buffer.
+                // (With three warpgroups each one waits on every phase of its own buffer and none of this is needed.)
+                if (kGroups == 2 && j > 0) {
+                    const int bq = (j - 1) % 3;
+                    mbar_wait(&s_full[bq], ((ph_base >> bq) ^ (uint32_t)((j - 1) / 3)) & 1u);
+                }
+                mbar_wait(&s_full[b], par);
+                tc_fence_after();
+                if (kProfile && (p.debug_flags & 8)) {          // tuning builds: barrier hand-offs only (wrong results)
+                    sMref[b * 128 + row] = 0.f;
+                    if (j > 0) sScale[b * 128 + row] = 1.f;
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(&mref_full[b]);
+                        if (j > 0) mbar_arrive(&sc_full[b]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(pv_ok_leader + b * 8);
+                    continue;
+                }
+                float sv[64];
+                auto load_half = [&](int hh) {
+                    tmem_ld_x32(s_addr + hh * 64 + 0, sv + 0);
+                    tmem_ld_x32(s_addr + hh * 64 + 32, sv + 32);
+                    tc_wait_ld();
+                    const int k0 = j * kBN + hh * 64;
+                    const bool need_mask = (k0 + 64 > nk) || (p.causal && (k0 + 63 > it.q0 + off));
+                    if (need_mask) {
+                        int vis = nk - 1 - k0;
+                        if (p.causal) vis = min(vis, q_row + off - k0);
+#pragma unroll
+                        for (int i = 0; i < 64; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
+                    }
+                };
+                auto max_of = [&]() -> float {
+                    float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
+#pragma unroll
+                    for (int i = 4; i < 64; i += 4) {
+                        mx0 = fmaxf(mx0, sv[i]);
+                        mx1 = fmaxf(mx1, sv[i + 1]);
+                        mx2 = fmaxf(mx2, sv[i + 2]);
+                        mx3 = fmaxf(mx3, sv[i + 3]);
+                    }
+                    return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+                };
+                load_half(0);
+                const float mxa = max_of();
+                load_half(1);
+                const float row_max = fmaxf(mxa, max_of());
+                // reference maximum after step j - 1 (posted by the other warpgroup); bring this thread's sum onto it
+                float m_ref = row_max;
+                float alpha = 1.f;
+                if (j > 0) {
+                    const int bp = (j - 1) % 3;
+                    mbar_wait(&mref_full[bp], ((ph_base >> bp) ^ (uint32_t)((j - 1) / 3)) & 1u);
+                    const float m_prev = sMref[bp * 128 + row];
+                    if (m_prev != m_own) d *= ex2_approx((m_own - m_prev) * cs);
+                    m_ref = m_prev;
+                    if ((row_max - m_prev) * cs > kRescaleThreshold) {
+                        alpha = ex2_approx((m_prev - row_max) * cs);
+                        m_ref = row_max;
+                        d *= alpha;
+                    }
+                }
+                m_own = m_ref;
+                sMref[b * 128 + row] = m_ref;
+                if (j > 0) sScale[b * 128 + row] = alpha;
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&mref_full[b]);
+                    if (j > 0) mbar_arrive(&sc_full[b]);
+                }
+                const float2 c2 = make_float2(cs, cs);
+                const float2 nmc2 = make_float2(-m_ref * cs, -m_ref * cs);
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+                auto exp_half = [&](int hh) {                   // P of keys [64 hh, +64) -> columns 64 + 32 hh .. of the buffer
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float2 x = ffma2(make_float2(sv[ch * 32 + 2 * i], sv[ch * 32 + 2 * i + 1]), c2, nmc2);
+                            float2 pv;
+                            if (i < kPolyPairs) {
+                                pv = exp2_poly2(x);
+                            } else {
+                                pv.x = ex2_approx(x.x);
+                                pv.y = ex2_approx(x.y);
+                            }
+                            if (i & 1) acc1 = fadd2(acc1, pv); else acc0 = fadd2(acc0, pv);
+                            pk[i] = pack2<kBf16>(pv.x, pv.y);
+                        }
+                        tmem_st_x16(s_addr + 64 + hh * 32 + ch * 16, pk);
+                    }
+                };
+                exp_half(1);
+                load_half(0);
+                exp_half(0);
+                acc0 = fadd2(acc0, acc1);
+                d += acc0.x + acc0.y;
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(pv_ok_leader + b * 8);
+            }
+            if (kGroups == 2 && ((it.n - 1) & 1) != g) {
+                // the item's last step belongs to the other warpgroup: see its S and its reference maximum complete
+                // before moving on, so that no barrier is ever more than one phase behind this warpgroup's next wait
+                const int bl = (it.n - 1) % 3;
+                const uint32_t pl = ((ph_base >> bl) ^ (uint32_t)((it.n - 1) / 3)) & 1u;
+                mbar_wait(&s_full[bl], pl);
+                mbar_wait(&mref_full[bl], pl);
+            }
+            mbar_wait(stats_free, item_par ^ 1);
+            sSum[g * 128 + row] = d;
+            sMax[g * 128 + row] = m_own * cs;                   // log2 units; -inf if this warpgroup had no step
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stats_full);
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb)
+                if (bb < it.n) ph_base ^= (uint32_t)(((it.n - bb + 2) / 3) & 1) << bb;
+        }
+    } else if (warp < R::kCorrWarp0 + 4) {
+        // =========================== correction + epilogue ===========================
+        if constexpr (kGroups == 2) reg_dealloc<96>();
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+        uint32_t sc_par = 0, item_cnt = 0, pvd_base = 0;
+        int peer_buf = 0;
+        if (peers.n > 0) peer_buf = (int)((*peers.epoch + 1u) & 1u);
+        if (lane == 0) mbar_arrive_cluster(pv_ok_leader);               // first item: O is free
+        for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, ++item_cnt) {
+            const WideItem it = decode_wide(w, p);
+            for (int j = 1; j < it.n; ++j) {
+                const int b = j % 3;
+                mbar_wait_relaxed(&sc_full[b], (sc_par >> b) & 1);
+                sc_par ^= 1u << b;
+                const float alpha = sScale[b * 128 + row];
+                const bool rescale = __any_sync(0xffffffffu, alpha != 1.f);
+                if (rescale) {
+                    // PV(j-1) must have completed before O is touched.  S runs up to two steps ahead of the PVs here, so a
+                    // single barrier could be two phases ahead of, or behind, a parity wait:
+                    // one barrier per step mod 3: PV(j-4) is known to be complete (S(j) complete implies PV(j-3) complete)
+                    // and PV(j+2) cannot have been issued, so the barrier of step j-1 is exactly in, or just past, the
+                    // phase waited for
+                    {
+                        const int bd = (j - 1) % 3;
+                        mbar_wait(&pv_done[bd], ((pvd_base >> bd) ^ (uint32_t)((j - 1) / 3)) & 1u);
+                    }
+                    tc_fence_after();
+#pragma unroll
+                    for (int ch = 0; ch < kD / 32; ++ch) {
+                        float orr[32];
+                        tmem_ld_x32(tmem_o + lane_addr + ch * 32, orr);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) orr[i] *= alpha;
+                        tmem_st_x32(tmem_o + lane_addr + ch * 32, orr);
+                    }
+                    tc_wait_st();
+                    tc_fence_before();
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(pv_ok_leader + b * 8);
+            }
+            // ---- epilogue ----
+            mbar_wait_relaxed(stats_full, item_cnt & 1);
+            mbar_wait_relaxed(o_final, item_cnt & 1);
+            tc_fence_after();
+            // the two warpgroups' partial sums, each relative to its own last reference maximum (log2 units)
+            float mlog2 = sMax[row];
+#pragma unroll
+            for (int gg = 1; gg < kGroups; ++gg) mlog2 = fmaxf(mlog2, sMax[gg * 128 + row]);
+            float dsum = 0.f;
+#pragma unroll
+            for (int gg = 0; gg < kGroups; ++gg) dsum += sSum[gg * 128 + row] * ex2_approx(sMax[gg * 128 + row] - mlog2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(stats_free);
+            const float inv = 1.f / dsum;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (warp == R::kCorrWarp0 && lane == 0) tma_store_wait_read<0>();
+                named_bar_sync(kBarEpilogue, 128);
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const int ch = hf * 2 + c2;
+                    float orr[32];
+                    tmem_ld_x32(tmem_o + lane_addr + ch * 32, orr);
+                    tc_wait_ld();
+                    if (ch == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(pv_ok_leader);   // O is in registers: the next item's PV(0) may run
+                    }
+                    uint8_t* srow = sO + row * 128;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 val;
+                        val.x = pack2<kBf16>(orr[8 * i + 0] * inv, orr[8 * i + 1] * inv);
+                        val.y = pack2<kBf16>(orr[8 * i + 2] * inv, orr[8 * i + 3] * inv);
+                        val.z = pack2<kBf16>(orr[8 * i + 4] * inv, orr[8 * i + 5] * inv);
+                        val.w = pack2<kBf16>(orr[8 * i + 6] * inv, orr[8 * i + 7] * inv);
+                        const int chunk = c2 * 4 + i;
+                        *reinterpret_cast<uint4*>(srow + ((chunk ^ (row & 7)) << 4)) = val;
+                    }
+                }
+                fence_proxy_async();
+                named_bar_sync(kBarEpilogue, 128);
+                if (warp == R::kCorrWarp0 && lane == 0) {
+                    if (peers.n == 0) {
+                        tma_store_4d(&map_o, sO, hf * 64, it.q0, it.h, it.b);
+                    } else {
+                        for (int r = 0; r < peers.n; ++r)
+                            tma_store_4d(&peers.maps[peer_buf][r], sO, hf * 64, it.q0, it.h + peers.head_offset,
+                                         it.b + peers.batch_offset);
+                    }
+                    tma_store_commit();
+                }
+            }
+            if (p.lse != nullptr && it.q0 + row < it.nq)
+                p.lse[it.b * p.lse_sb + it.h * p.lse_sh + it.q0 + row] = (mlog2 + log2f(dsum)) * kLn2;
+#pragma unroll
+            for (int bb = 0; bb < 3; ++bb)
+                if (bb < it.n) pvd_base ^= (uint32_t)(((it.n - bb + 2) / 3) & 1) << bb;
+        }
+        if (warp == R::kCorrWarp0 && lane == 0) tma_store_wait_all<0>();
+    } else {
+        reg_dealloc<64>();
+        if (warp == R::kMmaWarp && cta_rank == 0) {
+            // =========================== MMA issuer (leader CTA) ===========================
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t kLboK = 1u << 16;
+            constexpr uint32_t kLboV = (uint32_t)(kSubTileBytes >> 4) << 16;
+            const uint32_t q_lo = ((smem_u32(sQ) >> 4) & 0x3FFFu) | kLboK;
+            const uint32_t k_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboK;
+            const uint32_t v_lo = ((smem_u32(sKV) >> 4) & 0x3FFFu) | kLboV;
+            uint32_t kv_cnt = 0, item_par = 0, pv_par = 0;
+            auto commit = [&](uint64_t* bar) { umma2_commit_multicast(bar, (uint16_t)3); };
+            auto wait_entry = [&](uint32_t e) { mbar_wait(&kv_full[e % kRing], (e / kRing) & 1); };
+            auto issue_S = [&](int buf, uint32_t e) {
+                // this CTA's entry: keys [64 rank, +64) of the tile as two [64 rows][64 el] sub-tiles
+                const uint32_t ka = k_lo + (e % kRing) * (kEntryBytes >> 4);
+#pragma unroll
+                for (int ks = 0; ks < kD / 16; ++ks) {
+                    const uint32_t qoff = ((ks >> 2) * kSubTileBytes + (ks & 3) * 32) >> 4;
+                    const uint32_t koff = ((ks >> 2) * (kEntryBytes / 2) + (ks & 3) * 32) >> 4;
+                    umma2_ss_lohi(tmem_base + buf * 128, q_lo + qoff, ka + koff, kDescHi, kIdescS, ks > 0 ? 1u : 0u);
+                }
+            };
+            auto issue_PV = [&](int j, uint32_t e) {
+                // this CTA's entry: head_dim columns [64 rank, +64) of the tile's 128 keys (one sub-tile)
+                const uint32_t va = v_lo + (e % kRing) * (kEntryBytes >> 4);
+#pragma unroll
+                for (int ks = 0; ks < kBN / 16; ++ks)
+                    umma2_ts_lohi(tmem_o, tmem_base + (j % 3) * 128 + 64 + ks * 8, va + ks * (2048 >> 4), kDescHi, kIdescO,
+                                  (j > 0 || ks > 0) ? 1u : 0u);
+            };
+            for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
+                const WideItem it = decode_wide(w, p);
+                const int n = it.n;
+                mbar_wait(q_full, item_par);
+                const int n_pro = n < 3 ? n : 3;
+                for (int i = 0; i < n_pro; ++i) {
+                    const uint32_t e = kv_cnt++;
+                    wait_entry(e);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_S(i, e);
+                        commit(&s_full[i]);
+                        commit(&kv_empty[e % kRing]);
+                        if (i == n - 1) commit(q_empty);
+                    }
+                    __syncwarp();
+                }
+                for (int j = 0; j < n; ++j) {
+                    const int b = j % 3;
+                    const uint32_t ev = kv_cnt++;
+                    wait_entry(ev);
+                    const bool more = j + 3 < n;
+                    uint32_t ek = 0;
+                    if (more) {
+                        ek = kv_cnt++;
+                        wait_entry(ek);
+                    }
+                    mbar_wait(&pv_ok[b], (pv_par >> b) & 1);
+                    pv_par ^= 1u << b;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        issue_PV(j, ev);
+                        commit(&pv_done[b]);
+                        if (j == n - 1) commit(o_final);
+                        commit(&kv_empty[ev % kRing]);
+                        if (more) {
+                            issue_S(b, ek);
+                            commit(&s_full[b]);
+                            commit(&kv_empty[ek % kRing]);
+                            if (j + 3 == n - 1) commit(q_empty);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (warp == R::kTmaWarp && lane == 0) {
+            // =========================== TMA producer ===========================
+            prefetch_tensormap(&map_q);
+            prefetch_tensormap(&map_k);
+            prefetch_tensormap(&map_v);
+            prefetch_tensormap(&map_o);
+            const int rank = (int)cta_rank;
+            const uint32_t q_full_leader = mapa_u32(smem_u32(q_full), 0);
+            const uint32_t kv_full_leader = mapa_u32(smem_u32(kv_full), 0);
+            uint32_t kv_cnt = 0, item_par = 0;
+            for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, item_par ^= 1) {
+                const WideItem it = decode_wide(w, p);
+                auto acquire = [&]() -> uint32_t {
+                    const uint32_t e = kv_cnt++;
+                    mbar_wait_relaxed(&kv_empty[e % kRing], ((e / kRing) & 1) ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&kv_full[e % kRing], 2 * kEntryBytes);
+                    return e % kRing;
+                };
+                auto load_k = [&](int i) {          // keys [128 i + 64 rank, +64): map_k carries 64-row boxes
+                    const uint32_t s = acquire();
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf)
+                        tma_load_4d_pair(sKV + s * kEntryBytes + hf * (kEntryBytes / 2), &map_k, kv_full_leader + s * 8, hf * 64,
+                                         i * kBN + rank * 64, it.hk, it.b);
+                };
+                auto load_v = [&](int j) {          // head_dim columns [64 rank, +64) of keys [128 j, +128): 128-row boxes
+                    const uint32_t s = acquire();
+                    tma_load_4d_pair(sKV + s * kEntryBytes, &map_v, kv_full_leader + s * 8, rank * 64, j * kBN, it.hk, it.b);
+                };
+                mbar_wait_relaxed(q_empty, item_par ^ 1);
+                if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * kTileBytes);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+                    tma_load_4d_pair(sQ + hf * kSubTileBytes, &map_q, q_full_leader, hf * 64, it.q0, it.h, it.b);
+                const int n_pro = it.n < 3 ? it.n : 3;
+                for (int i = 0; i < n_pro; ++i) load_k(i);
+                for (int j = 0; j < it.n; ++j) {
+                    load_v(j);
+                    if (j + 3 < it.n) load_k(j + 3);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------
 // UMMA self-test (debug aid, exported as pli_debug_umma_selftest): one 128x128xD tile through the
 // exact descriptor / TMEM paths the prefill kernel uses.  S = A B^T (SS, K-major), then
@@ -886,6 +1413,14 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 // CTA-pair MMAs are opt-in (PLI_PAIR_MMA=1 in the environment, or bit 1 of pli_debug_prefill_trace's flags): measured
 // equal to per-CTA MMAs + TMA multicast on the whole chip (1287-1292 vs 1288-1294 TFLOP/s on C2) and 2.5 % slower per SM
 // on part of it, so the simpler protocol stays the default.
+bool wide_env() {                       // PLI_WIDE=1: the one-tile, 128-key-step kernel (prefill_wide_kernel)
+    static const bool on = [] {
+        const char* e = getenv("PLI_WIDE");
+        return e && e[0] == '1';
+    }();
+    return on;
+}
+
 bool pair_mma_env() {
     static const bool on = [] {
         const char* e = getenv("PLI_PAIR_MMA");
@@ -956,6 +1491,38 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mq, mk, mv, mo, p, peers));
+    count_launch();
+    return PLI_OK;
+}
+
+template <bool kBf16, int kGroups>
+int launch_wide(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
+                const PrefillParams& p, cudaStream_t stream, const PeerMaps& peers) {
+    auto kern = prefill_wide_kernel<kBf16, kGroups>;
+    const int smem = WideLayout::kTotal + 1024;
+    PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
+    int grid = sm_count();
+    if (grid <= 0) grid = 148;
+    static const int max_ctas = [] {
+        const char* e = getenv("PLI_MAX_CTAS");
+        return e ? atoi(e) : 0;
+    }();
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (grid > p.total_items) grid = p.total_items;
+    grid -= grid % 2;                                   // total_items is even (even group size)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(WideRoles<kGroups>::kThreadsWide);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -1090,6 +1657,38 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
     // pair MMAs (D = 128): each CTA loads 32-key boxes of K and full-height, 64-column boxes of V (its half of B)
     const bool pair_mma = pairs && D == 128 && (pair_mma_env() || (g_debug_flags & 2));
+    // one Q tile per CTA, 128-key S tiles, pair MMAs (any even group size): opt-in
+    const bool wide = D == 128 && (Hq / Hkv) % 2 == 0 && cluster_mode_enabled() && (wide_env() || (g_debug_flags & 4));
+    if (wide) {
+        if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, kHN))) return rc;
+        if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, kBN))) return rc;
+        if (peer != nullptr) mo = pm.maps[0][0];
+        else if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
+        PrefillParams p;
+        p.lse = lse;
+        p.B = B;
+        p.Hq = Hq;
+        p.Hkv = Hkv;
+        p.Nq = Nq;
+        p.Nk = Nk;
+        p.causal = causal;
+        p.scale = scale;
+        p.scale_log2 = scale * kLog2e;
+        fill_schedule(p, B, Hq, Hkv, Nq);
+        p.head_pairs = 0;
+        p.num_pairs = (Nq + kBM - 1) / kBM;                       // 128-row slots; one item per (q head, slot)
+        const int64_t total = (int64_t)B * Hq * p.num_pairs;
+        if (total > 0x7fffffff) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
+        p.total_items = (int)total;
+        const int sms = sm_count() > 0 ? sm_count() : 148;
+        p.pair_block = total >= (int64_t)32 * sms ? 8 : 4;
+        if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
+        if (g_debug_flags & 32)              // two softmax warpgroups (512 threads) instead of three
+            return dtype == PLI_BF16 ? launch_wide<true, 2>(mq, mk, mv, mo, p, stream, pm)
+                                     : launch_wide<false, 2>(mq, mk, mv, mo, p, stream, pm);
+        return dtype == PLI_BF16 ? launch_wide<true, 3>(mq, mk, mv, mo, p, stream, pm)
+                                 : launch_wide<false, 3>(mq, mk, mv, mo, p, stream, pm);
+    }
     if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pair_mma ? kHN / 2 : pairs ? kHN : kBN))) return rc;
     if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pair_mma ? kBN : pairs ? kHN : kBN))) return rc;
     if (peer != nullptr) mo = pm.maps[0][0];
