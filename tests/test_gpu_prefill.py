@@ -252,6 +252,45 @@ def test_pair_mma_variant_matches_default_bitwise(shape, causal, dtype):
     assert (l1.cpu() - rl).abs().max().item() <= 1e-3
 
 
+@pytest.mark.parametrize("flags", [4, 36])          # 4: three softmax warpgroups (576 threads), 36: two (512 threads)
+@pytest.mark.parametrize("shape,causal", [
+    ((1, 2, 1, 128, 128, 128), True),        # one step, one pair of CTAs
+    ((1, 4, 1, 300, 300, 128), True),        # ragged last tile and last step
+    ((2, 8, 2, 1024, 1024, 128), True),      # rescales at many steps (inputs below), items of 1..8 steps
+    ((2, 8, 2, 1024, 1024, 128), False),
+    ((1, 8, 2, 129, 1000, 128), True),       # chunk over cache: offset mask, 8 steps for a 2-tile chunk
+    ((1, 6, 3, 513, 513, 128), True),        # group size 2
+    ((4, 32, 8, 256, 256, 128), False),      # more items than CTAs
+    ((1, 8, 2, 2048, 2048, 128), True),
+])
+def test_wide_kernel_variant_parity(shape, causal, flags):
+    """The opt-in wide kernel (prefill_wide_kernel: one 128-row Q tile per CTA, 128-key S tiles in three TMEM buffers,
+    CTA-pair MMAs, softmax warpgroups taking alternate steps with the reference maximum handed from step to step): oracle
+    tolerance, closeness to the default kernel, bitwise run-to-run reproducibility (its barrier protocol is new)."""
+    from physics_llm_inference_b200 import _lib
+    lib = _lib.load()
+    B, Hq, Hkv, Nq, Nk, D = shape
+    q, k, v = orc.seeded_qkv(91, B, Hq, Hkv, Nq, Nk, D)
+    k = k * torch.linspace(0.5, 4.0, Nk).view(1, 1, Nk, 1)
+    qd, kd, vd = q.bfloat16().cuda(), k.bfloat16().cuda(), v.bfloat16().cuda()
+    o0, l0 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
+    torch.cuda.synchronize()
+    try:
+        _lib.check(lib.pli_debug_prefill_trace(None, 0, flags))
+        o1, l1 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
+        torch.cuda.synchronize()
+        for _ in range(8):
+            o2, l2 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
+            torch.cuda.synchronize()
+            assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    finally:
+        _lib.check(lib.pli_debug_prefill_trace(None, 0, 0))
+    ro, rl = orc.flash_attention_oracle(qd, kd, vd, causal=causal)
+    assert (o1.float().cpu() - ro).abs().max().item() <= 2e-2
+    assert (l1.cpu() - rl).abs().max().item() <= 1e-3
+    assert (o1.float() - o0.float()).abs().max().item() <= 4e-2      # two bf16 roundings apart at most
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("bs,D,Hkv,G,Nq,lens", [
     (16, 128, 2, 4, 128, [512, 300, 128]),          # C3-style pages, cluster pairs (G % 4 == 0), ragged cache lengths

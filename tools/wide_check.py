@@ -1,5 +1,5 @@
-"""Bring-up check of the opt-in wide prefill kernel (flags bit 2 of pli_debug_prefill_trace) against the default kernel
-and the oracle: python tools/wide_check.py"""
+"""Bring-up check of the opt-in wide prefill kernel (flags bit 2 of pli_debug_prefill_trace; argv[1] = flags, default 4 =
+three softmax warpgroups, 36 = two) against the default kernel and the oracle: python tools/wide_check.py [flags]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,6 +8,7 @@ from physics_llm_inference_b200 import _lib
 from oracle import attention_oracle as orc
 
 lib = _lib.load()
+FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 shapes = [((1, 2, 1, 128, 128, 128), True), ((1, 2, 1, 128, 128, 128), False), ((1, 4, 1, 256, 256, 128), True),
           ((1, 4, 1, 300, 300, 128), True), ((2, 8, 2, 1024, 1024, 128), True), ((2, 8, 2, 1024, 1024, 128), False),
           ((1, 8, 2, 129, 1000, 128), True), ((2, 16, 2, 384, 1000, 128), True), ((1, 8, 2, 2048, 2048, 128), True),
@@ -20,7 +21,7 @@ for (B, Hq, Hkv, Nq, Nk, D), causal in shapes:
     o0, l0 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
     torch.cuda.synchronize()
     try:
-        _lib.check(lib.pli_debug_prefill_trace(None, 0, 4))
+        _lib.check(lib.pli_debug_prefill_trace(None, 0, FLAGS))
         o1, l1 = pli.flash_attention_forward(qd, kd, vd, causal=causal, return_lse=True)
         torch.cuda.synchronize()
         same = True
