@@ -75,8 +75,9 @@ void pli_reset_launch_count(void);
  *
  *   q  (B,Hq,Nq,D)   k,v (B,Hkv,Nk,D)   o (B,Hq,Nq,D) same dtype as q   lse (B,Hq,Nq) f32 or NULL
  *   *_strides[3] = {batch, head, token} element strides; head_dim stride is 1.
- *   bf16/f16 with D in {64,128}: tcgen05 kernel (needs 16-byte aligned pointers and strides that
- *   are multiples of 8 elements).  Anything else with D <= 256: SIMT kernel.
+ *   bf16/f16 with D in {64,128}: tcgen05 kernel (needs 16-byte aligned pointers and non-zero strides that
+ *   are multiples of 8 elements; a broadcast / zero stride cannot be described by a TMA tensor map).
+ *   Anything else with D <= 256: SIMT kernel, which indexes with the strides exactly as given.
  * ------------------------------------------------------------------------------------------- */
 int pli_prefill_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                     int B, int Hq, int Hkv, int Nq, int Nk, int D,
@@ -92,8 +93,9 @@ int pli_prefill_fwd(const void* q, const void* k, const void* v, void* o, float*
  *   q, o (B,Hq,Nq,D) strides {batch, head, token};  pools / block_table / kv_strides / layer as for decode;
  *   seq_lens (B,) int32 device: cached length of each sequence INCLUDING the Nq new tokens;
  *   max_seq_len: host upper bound;  bf16/f16, D in {64,128}, block_size in {16,32,64,128}.
- * Slots of a sequence's last page past seq_lens[b] are read (and masked): they must hold finite values, which
- * the reference's zero-initialised pools (ch07/paged_memory.py:44-47) guarantee. */
+ * Storage past seq_lens[b] (the rest of a sequence's last page, unused pages) may hold anything, NaN/Inf included:
+ * the reference's allocator recycles pages without clearing them (ch07/paged_memory.py:100-110).  Scores of those
+ * keys are replaced by select and their V rows are zeroed in shared memory before any MMA reads them. */
 int pli_prefill_paged_fwd(const void* q, const void* k_pool, const void* v_pool,
                           const int32_t* block_table, const int32_t* seq_lens, void* o, float* lse,
                           int B, int Hq, int Hkv, int Nq, int D, int max_seq_len,
@@ -236,6 +238,23 @@ int pli_kv_append(const void* k_new, const void* v_new, void* k_store, void* v_s
 int pli_paged_gather(const void* store, void* out, const int32_t* block_table, const int32_t* seq_lens,
                      int B, int max_len, int Hkv, int D, int block_size, int table_stride, int layer,
                      const int64_t kv_strides[4], int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The scalar online-softmax recurrence on its own (ch06/online_softmax.py).
+ *
+ * pli_online_softmax replaces `online_softmax(x)` (:13-25): softmax over the last dimension through the running
+ * (max, sum) update  m' = max(m, x_i),  d' = d*exp(m - m') + exp(x_i - m').
+ * pli_online_softmax_with_output replaces `online_softmax_with_output(x, v)` (:28-53): the same with the running
+ * weighted sum  o' = (o*d*exp(m - m') + v_i*exp(x_i - m')) / d';  writes o (rows, dv) and d (rows,) = sum_i exp(x_i - max).
+ *   x (rows, n), out (rows, n), v (rows, n, dv), o (rows, dv): leading dimensions flattened to `rows`;
+ *   *_row_stride = elements between consecutive rows, v_elem_stride = elements between consecutive i; innermost
+ *   strides are 1.  f32 / bf16 / f16; fp32 arithmetic.  dv <= 256.
+ * ------------------------------------------------------------------------------------------- */
+int pli_online_softmax(const void* x, void* out, int64_t rows, int n, int64_t x_row_stride, int64_t out_row_stride,
+                       int dtype, void* stream);
+int pli_online_softmax_with_output(const void* x, const void* v, void* o, float* d, int64_t rows, int n, int dv,
+                                   int64_t x_row_stride, int64_t v_row_stride, int64_t v_elem_stride,
+                                   int64_t o_row_stride, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -67,6 +67,9 @@ _SIGNATURES = {
                                 C.c_int, _I64P, _I64P, C.c_int, _VP]),
     "pli_paged_gather": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    _I64P, C.c_int, _VP]),
+    "pli_online_softmax": (C.c_int, [_VP, _VP, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_int, _VP]),
+    "pli_online_softmax_with_output": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                                 C.c_int64, C.c_int64, C.c_int, _VP]),
     # debug aid, not declared in the public header
     "pli_debug_umma_selftest": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "pli_debug_prefill_trace": (C.c_int, [_VP, C.c_int, C.c_int]),

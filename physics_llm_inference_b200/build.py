@@ -20,7 +20,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libpli_attention.so")
 
-SOURCES = ["pli_capi.cu", "prefill_tcgen05.cu", "prefill_simt.cu", "decode.cu"]
+SOURCES = ["pli_capi.cu", "prefill_tcgen05.cu", "prefill_simt.cu", "decode.cu", "online_softmax.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(ROOT, "include", "pli_attention.h")]
 
 NVCC_FLAGS = [
@@ -76,7 +76,7 @@ def build(force: bool = False, verbose: bool = False, variant: str = "", defines
         if force or _stale(obj, [src, *HEADERS]):
             jobs.append((src, obj))
     if jobs:
-        with ThreadPoolExecutor(max_workers=min(4, len(jobs))) as ex:
+        with ThreadPoolExecutor(max_workers=min(5, len(jobs))) as ex:
             list(ex.map(lambda so: _compile(nvcc, so[0], so[1], verbose, tuple(defines)), jobs))
     if force or jobs or _stale(lib, objs):
         cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]

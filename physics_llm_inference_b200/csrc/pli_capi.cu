@@ -93,8 +93,10 @@ static bool tcgen05_eligible(int D, int dtype, const int64_t* qs, const int64_t*
         if (qs[i] % 8 || ks[i] % 8 || vs[i] % 8 || os[i] % 8) return false;
         if (qs[i] < 0 || ks[i] < 0 || vs[i] < 0 || os[i] < 0) return false;
     }
-    // token strides must be real (TMA cannot broadcast a zero stride)
-    if (qs[2] == 0 || ks[2] == 0 || vs[2] == 0 || os[2] == 0) return false;
+    // every stride must be real: TMA cannot broadcast, so expanded (zero-stride) views such as k.expand(B, ...) or an
+    // MQA k[:, :1].expand(-1, H, -1, -1) go to the SIMT kernel, which indexes with the strides as given
+    for (int i = 0; i < 3; ++i)
+        if (qs[i] == 0 || ks[i] == 0 || vs[i] == 0 || os[i] == 0) return false;
     return true;
 }
 
@@ -208,6 +210,12 @@ extern "C" int pli_prefill_paged_fwd(const void* q, const void* k_pool, const vo
     for (int i = 0; i < 3; ++i)
         if (q_strides[i] % 8 || o_strides[i] % 8 || q_strides[i] < 0 || o_strides[i] < 0)
             return set_error(PLI_ERR_INVALID, "q/o strides must be non-negative multiples of 8 elements");
+    {
+        const int sizes[3] = {B, Hq, Nq};
+        for (int i = 0; i < 3; ++i)
+            if (sizes[i] > 1 && (q_strides[i] == 0 || o_strides[i] == 0))
+                return set_error(PLI_ERR_UNSUPPORTED, "paged prefill cannot read an expanded (zero-stride) q; make it contiguous");
+    }
     for (int i = 0; i < 4; ++i)
         if (kv_strides[i] % 8 || kv_strides[i] < 0) return set_error(PLI_ERR_INVALID, "pool strides must be multiples of 8 elements");
     return launch_prefill_tcgen05_paged(q, k_pool, v_pool, block_table, seq_lens, nullptr, 0, o, lse, B, Hq, Hkv, Nq, D,

@@ -32,14 +32,26 @@ constexpr int kBN = 128;               // keys per KV tile
 constexpr int kThreads = 512;
 constexpr int kSubTileBytes = 128 * 128;  // [128 rows][64 el] bf16
 constexpr float kRescaleThreshold = 8.f;  // log2 units: rescale O only when the max grew by more
+// Measured with the correction warps sharing the exponentials (round 2, C2 causal, same box): 0 pairs 1268-1276 TFLOP/s,
+// 2 pairs 1256-1274, 4 pairs 1230, 6 pairs 1211: with three busy warps per scheduler the issue slots are the scarce
+// resource, and a polynomial exp2 costs ~8 issue cycles per element against 1 for MUFU.EX2.
 #ifndef PLI_POLY_PAIRS
-#define PLI_POLY_PAIRS 4
+#define PLI_POLY_PAIRS 0
 #endif
-constexpr int kPolyPairs = PLI_POLY_PAIRS;
+constexpr int kPolyPairs = PLI_POLY_PAIRS;   // of every 16 element pairs, how many take the polynomial exp2
+// Of every 64-key half-step s >= 1, the LAST kCorrCols score columns of a row are exponentiated by the correction warp
+// of the same TMEM lane quadrant instead of the softmax warp (which still reads all 64 columns for the row maximum):
+// the softmax warps' serial time per half-step is what bounds the kernel, the four correction warps
+// are otherwise idle, and three warps per scheduler hide each other's TMEM / MUFU latencies better than two.
+#ifndef PLI_CORR_COLS
+#define PLI_CORR_COLS 16
+#endif
+constexpr int kCorrCols = PLI_CORR_COLS;
+static_assert(kCorrCols == 0 || kCorrCols == 16 || kCorrCols == 32, "kCorrCols: 0, 16 or 32 of the 64 columns");
 #ifndef PLI_PROFILE
 #define PLI_PROFILE 0                     // 1: compile the in-kernel timeline / phase counters (tuning builds only)
 #endif
-constexpr bool kProfile = PLI_PROFILE != 0;  // of every 16 element pairs, how many take the polynomial exp2
+constexpr bool kProfile = PLI_PROFILE != 0;
 
 // named barrier ids (0 is __syncthreads)
 constexpr int kBarEpilogue = 1;
@@ -54,7 +66,8 @@ struct SmemLayout {
     static constexpr int kScaleOff = kOOff + kSubTileBytes;        // float [2 tiles][2 buffers][128]
     static constexpr int kSumOff = kScaleOff + 4 * 128 * 4;        // float [2][128]
     static constexpr int kMaxOff = kSumOff + 2 * 128 * 4;          // float [2][128]
-    static constexpr int kBarOff = kMaxOff + 2 * 128 * 4;
+    static constexpr int kNmcOff = kMaxOff + 2 * 128 * 4;          // float [2 tiles][2 buffers][128]: -m_ref * c of the step
+    static constexpr int kBarOff = kNmcOff + 4 * 128 * 4;
     static constexpr int kNumBars = 4 + 4 * kKVStages + 22;       // the K/V ring has 2 x kKVStages half-size entries with pair MMAs
     static constexpr int kTmemPtrOff = kBarOff + kNumBars * 8;
     static constexpr int kTotal = kTmemPtrOff + 16;
@@ -114,6 +127,26 @@ __device__ __forceinline__ void trace_event(const PrefillParams& p, int lane, in
 }
 
 constexpr int kHN = 64;                // keys per softmax / MMA half-step (half of a KV tile)
+
+// P = exp2(S * c - m * c) for 16 scores of a row: packed FFMA2 for the argument, MUFU.EX2 (an FMA-pipe polynomial for
+// kPolyPairs of every 16 pairs), row sums in two packed FADD2 chains, bf16/f16 pairs packed into pk[0..8).
+template <bool kBf16>
+__device__ __forceinline__ void exp_chunk16(const float* sv, float2 c2, float2 nmc2, float2& acc0, float2& acc1,
+                                            uint32_t* pk) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float2 x = ffma2(make_float2(sv[2 * i], sv[2 * i + 1]), c2, nmc2);
+        float2 pv;
+        if (i < kPolyPairs / 2) {
+            pv = exp2_poly2(x);
+        } else {
+            pv.x = ex2_approx(x.x);
+            pv.y = ex2_approx(x.y);
+        }
+        if (i & 1) acc1 = fadd2(acc1, pv); else acc0 = fadd2(acc0, pv);
+        pk[i] = pack2<kBf16>(pv.x, pv.y);
+    }
+}
 
 __device__ __forceinline__ int half_steps_for(int q0_tile, const PrefillParams& p, int nk, int nq) {
     // number of 64-key half-steps a Q tile starting at row q0_tile attends to (>= 1; a tile past the last query
@@ -228,6 +261,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     float* sScale = reinterpret_cast<float*>(smem + L::kScaleOff);   // [2 tiles][2 buffers][128]
     float* sSum = reinterpret_cast<float*>(smem + L::kSumOff);       // [2][128]
     float* sMax = reinterpret_cast<float*>(smem + L::kMaxOff);       // [2][128]
+    float* sNmc = reinterpret_cast<float*>(smem + L::kNmcOff);       // [2 tiles][2 buffers][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
     uint64_t* q_full = bars;                  // [2]      TMA -> MMA warp t
     uint64_t* q_empty = bars + 2;             // [2]      MMA warp t (commit) -> TMA
@@ -357,34 +391,35 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     m_ref = m_new;
                     d *= alpha;
                 }
+                const float nmc = -m_ref * c;
                 if (s > 0) {
                     sScale[(t * 2 + h) * 128 + row] = alpha;
+                    if constexpr (kCorrCols > 0) sNmc[(t * 2 + h) * 128 + row] = nmc;
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sc_full[t * 2 + h]);
                 }
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 2, t, s);       // max known, scale factor posted
-                // P = exp2(S*c - m*c): packed FFMA2 for the argument, MUFU.EX2 (optionally an FMA-pipe polynomial
-                // for kPolyPairs of every 16 pairs), row sums in packed FADD2 chains.
+                // P = exp2(S*c - m*c) in 16-column chunks; P aliases the first 32 columns of its S buffer (8 per chunk).
+                // From half-step 1 on, the last kCorrCols columns are left to the correction warp of this lane quadrant.
                 const float2 c2 = make_float2(c, c);
-                const float2 nmc2 = make_float2(-m_ref * c, -m_ref * c);
+                const float2 nmc2 = make_float2(nmc, nmc);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
+                const int n_chunks = s > 0 ? (kHN - kCorrCols) / 16 : 4;                // warp-uniform
+                {
                     uint32_t pk[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float2 x = ffma2(make_float2(sv[ch * 32 + 2 * i], sv[ch * 32 + 2 * i + 1]), c2, nmc2);
-                        float2 pv;
-                        if (i < kPolyPairs) {
-                            pv = exp2_poly2(x);
-                        } else {
-                            pv.x = ex2_approx(x.x);
-                            pv.y = ex2_approx(x.y);
-                        }
-                        if (i & 1) acc1 = fadd2(acc1, pv); else acc0 = fadd2(acc0, pv);
-                        pk[i] = pack2<kBf16>(pv.x, pv.y);
-                    }
-                    tmem_st_x16(s_addr + ch * 16, pk);    // P aliases the first 32 columns of its S buffer
+                    exp_chunk16<kBf16>(sv + 0, c2, nmc2, acc0, acc1, pk);
+                    exp_chunk16<kBf16>(sv + 16, c2, nmc2, acc0, acc1, pk + 8);
+                    tmem_st_x16(s_addr, pk);
+                }
+                if (kCorrCols < 32 || n_chunks > 2) {
+                    uint32_t pk[8];
+                    exp_chunk16<kBf16>(sv + 32, c2, nmc2, acc0, acc1, pk);
+                    tmem_st_x8(s_addr + 16, pk);
+                }
+                if (kCorrCols < 16 || n_chunks > 3) {
+                    uint32_t pk[8];
+                    exp_chunk16<kBf16>(sv + 48, c2, nmc2, acc0, acc1, pk);
+                    tmem_st_x8(s_addr + 24, pk);
                 }
                 acc0 = fadd2(acc0, acc1);
                 d += acc0.x + acc0.y;
@@ -419,15 +454,52 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         }
         for (int rnd = 0, w; (w = item_of_round(rnd, p)) >= 0; ++rnd, ++item_cnt) {
             const WorkItem it = decode_item(w, p);
+            float d_corr[2] = {0.f, 0.f};                 // row sums of the columns this warp exponentiates (per Q tile)
             for (int s = 1; s < it.n[1]; ++s) {
                 const int h = s & 1;
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
                     if (s >= it.n[t]) continue;
                     const int bi = t * 2 + h;
+#if defined(PLI_CORR_SPIN) && PLI_CORR_SPIN
+                    mbar_wait(&sc_full[bi], (sc_par >> bi) & 1);
+#else
                     mbar_wait_relaxed(&sc_full[bi], (sc_par >> bi) & 1);
+#endif
                     sc_par ^= 1u << bi;
                     const float alpha = sScale[bi * 128 + row];
+                    if constexpr (kCorrCols > 0) {
+                        // this warp's share of P_t(s): columns [64 - kCorrCols, 64) of the S buffer (the softmax warp has
+                        // read the whole row and posted -m_ref * c next to the scale factor)
+                        const float nmc = sNmc[bi * 128 + row];
+                        const float cs = p.scale_log2;
+                        const uint32_t s_addr = tmem_base + t * 128 + h * 64 + lane_addr;
+                        tc_fence_after();
+                        float sv[kCorrCols];
+#pragma unroll
+                        for (int cc = 0; cc < kCorrCols / 16; ++cc)
+                            tmem_ld_x16(s_addr + (kHN - kCorrCols) + cc * 16, sv + cc * 16);
+                        tc_wait_ld();
+                        const int k0 = s * kHN, off = it.nk - it.nq;
+                        const bool need_mask = (k0 + kHN > it.nk) || (p.causal && (k0 + kHN - 1 > it.q0[t] + off));
+                        if (need_mask) {
+                            int vis = it.nk - 1 - k0;
+                            if (p.causal) vis = min(vis, it.q0[t] + row + off - k0);
+                            vis -= kHN - kCorrCols;
+#pragma unroll
+                            for (int i = 0; i < kCorrCols; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
+                        }
+                        const float2 c2 = make_float2(cs, cs), nmc2 = make_float2(nmc, nmc);
+                        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int cc = 0; cc < kCorrCols / 16; ++cc) {
+                            uint32_t pk[8];
+                            exp_chunk16<kBf16>(sv + cc * 16, c2, nmc2, acc0, acc1, pk);
+                            tmem_st_x8(s_addr + (kHN - kCorrCols) / 2 + cc * 8, pk);
+                        }
+                        acc0 = fadd2(acc0, acc1);
+                        d_corr[t] = d_corr[t] * alpha + (acc0.x + acc0.y);
+                    }
                     const bool rescale = __any_sync(0xffffffffu, alpha != 1.f);
                     if (rescale) {
                         // PV_t(s-1) must have completed: covered by the commit behind S_t(s+1), or by pv_tail
@@ -449,6 +521,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                         tc_wait_st();
                         tc_fence_before();
+                    } else if constexpr (kCorrCols > 0) {
+                        tc_wait_st();
+                        tc_fence_before();
                     }
                     __syncwarp();
                     if (lane == 0) arrive_pv_ok(bi);
@@ -461,7 +536,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 mbar_wait_relaxed(&o_final[t], item_cnt & 1);
                 mbar_wait_relaxed(&pv_tail[t], item_cnt & 1);         // one phase per item: keeps its parity in step
                 tc_fence_after();
-                const float dsum = sSum[t * 128 + row];
+                const float dsum = sSum[t * 128 + row] + d_corr[t];
                 const float mlog2 = sMax[t * 128 + row];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stats_free[t]);
@@ -621,6 +696,24 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 for (int s = 0; s < nt; ++s) {
                     const int h = s & 1;
                     if (h == 0) wait_kv(2 * (s >> 1) + 1);                           // V tile of this pair of half-steps
+                    if constexpr (kPaged) {
+                        // Rows of the V tile at or beyond the sequence end hold whatever the (recycled, never cleared:
+                        // ch07/paged_memory.py:100-110) page holds, and 0 x NaN would poison the row: zero them in shared
+                        // memory before the first PV that reads the tile.  Both MMA warps do it (same zeros), each
+                        // before its own MMAs.  K needs nothing: scores of those keys are replaced by select.
+                        const int r0 = max(it.nk - (s >> 1) * kBN, 0);
+                        if (h == 0 && r0 < kBN) {
+                            uint8_t* vt = sKV + slot_of(2 * (s >> 1) + 1) * kTileBytes;
+                            const int rows = kBN - r0;
+                            for (int idx = lane; idx < rows * 8 * kHalves; idx += 32) {
+                                const int chunk = idx & 7, rr = idx >> 3;
+                                const int hf = rr / rows, r = r0 + rr - hf * rows;
+                                *reinterpret_cast<uint4*>(vt + hf * kSubTileBytes + r * 128 + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
+                            }
+                            fence_proxy_async();
+                            __syncwarp();
+                        }
+                    }
                     const bool more = s + 2 < nt;
                     if (more && h == 0) wait_kv(2 * ((s + 2) >> 1));                 // K tile of the S two half-steps ahead
                     mbar_wait(&pv_ok[t * 2 + h], (pv_par >> h) & 1);
@@ -1449,6 +1542,12 @@ int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int
     const CUtensorMapDataType dt = dtype == PLI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     // dims fastest first: head_dim, token, head, batch; a broadcast (zero) stride on a size-1 dim is replaced
     cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+    // TMA cannot broadcast: a zero (expanded) stride is only acceptable on a dimension of size 1, where it is never used
+    const int sizes[3] = {B, H, N};
+    for (int i = 0; i < 3; ++i)
+        if (st[i] <= 0 && sizes[i] > 1)
+            return set_error(PLI_ERR_UNSUPPORTED, "stride %lld on a dimension of size %d cannot be described by a tensor map",
+                             (long long)st[i], sizes[i]);
     auto fix = [&](int64_t s) -> cuuint64_t { return (cuuint64_t)(s > 0 ? s : (int64_t)D) * 2; };
     cuuint64_t strides[3] = {fix(st[2]), fix(st[1]), fix(st[0])};
     cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};

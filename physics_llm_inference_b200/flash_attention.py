@@ -34,7 +34,14 @@ class FlashAttentionConfig:
 
 
 def _unit_inner(x: torch.Tensor) -> torch.Tensor:
-    return x if x.stride(-1) == 1 else x.contiguous()
+    """Views the tensor-core kernels can read in place: unit head_dim stride and no broadcast (zero) stride on a
+    dimension larger than one (TMA cannot broadcast; `k.expand(...)` would otherwise fall to the slow SIMT kernel)."""
+    if x.stride(-1) != 1:
+        return x.contiguous()
+    for size, stride in zip(x.shape[:-1], x.stride()[:-1]):
+        if size > 1 and stride == 0:
+            return x.contiguous()
+    return x
 
 
 def _check_inputs(q, k, v):

@@ -10,6 +10,7 @@ import torch
 
 import physics_llm_inference_b200 as pli
 from oracle import attention_oracle as orc
+from physics_llm_inference_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -379,3 +380,106 @@ def test_prefill_peer_output_single_rank():
     for step in range(3):
         o, lse = pli.flash_attention_forward(q, k, v, causal=True, return_lse=True, peer_out=po)
         assert torch.equal(o, ref) and torch.equal(lse, rlse), step
+
+
+def _poison_unused(kp, vp, table, lens, bs, layer):
+    """NaN into K and Inf into V wherever no sequence has a token: the rest of each last page and every unused page
+    (the reference's allocator recycles pages without clearing them, ch07/paged_memory.py:100-110)."""
+    used = torch.zeros(kp.shape[0], bs, dtype=torch.bool)
+    for b, L in enumerate(lens):
+        for t in range(L):
+            used[int(table[b, t // bs]), t % bs] = True
+    kp[:, layer][~used.to(kp.device)] = float("nan")
+    vp[:, layer][~used.to(vp.device)] = float("inf")
+
+
+@pytest.mark.parametrize("bs,D,Hkv,G,Nq,lens", [
+    (16, 128, 2, 4, 128, [500, 300, 129]),          # CTA pairs; last pages 4, 12 and 1 tokens full
+    (16, 128, 1, 2, 70, [777, 71]),                 # head pairs, single CTA
+    (64, 64, 2, 1, 96, [1000, 97, 641]),            # big pages: most of the last page is garbage
+    (128, 128, 1, 4, 33, [130, 33]),                # one-page tiles
+])
+def test_paged_prefill_ignores_garbage_past_seq_len(bs, D, Hkv, G, Nq, lens):
+    """Recycled pages are dirty: NaN/Inf beyond seq_lens[b] must not change a single bit of the paged prefill output
+    (keys are masked by select, V rows past the end are zeroed in shared memory before the MMAs read them)."""
+    B, Hq = len(lens), Hkv * G
+    _, kp, vp, table, lens_t = orc.seeded_paged(81, B, Hq, Hkv, D, bs, lens, num_layers=2, dtype=torch.bfloat16)
+    q = torch.randn(B, Hq, Nq, D, generator=torch.Generator().manual_seed(82)).bfloat16().cuda()
+    kd, vd = kp.cuda(), vp.cuda()
+    args = (table.cuda(), lens_t.cuda())
+    o0, l0 = pli.flash_attention_paged(q, kd, vd, *args, layer=1, return_lse=True, max_seq_len=max(lens))
+    _poison_unused(kd, vd, table, lens, bs, 1)
+    o1, l1 = pli.flash_attention_paged(q, kd, vd, *args, layer=1, return_lse=True, max_seq_len=max(lens))
+    assert torch.isfinite(o1.float()).all()
+    assert torch.equal(o0, o1) and torch.equal(l0, l1)
+    ro, _ = orc.paged_decode_oracle(q.cpu(), kp, vp, table, lens_t, layer=1)
+    assert (o1.float().cpu() - ro).abs().max().item() <= 2e-2
+
+
+def test_varlen_and_mixed_batch_ignore_garbage_past_seq_len():
+    bs, D, Hkv, G = 16, 128, 2, 4
+    Hq = Hkv * G
+    q_lens, lens = [128, 37, 300, 1], [500, 300, 301, 77]
+    _, kp, vp, table, lens_t = orc.seeded_paged(83, len(lens), Hq, Hkv, D, bs, lens, dtype=torch.bfloat16)
+    T = sum(q_lens)
+    q = torch.randn(T, Hq, D, generator=torch.Generator().manual_seed(84)).bfloat16().cuda()
+    cu = torch.tensor([0] + q_lens, dtype=torch.int32).cumsum(0, dtype=torch.int32).cuda()
+    kd, vd = kp.cuda(), vp.cuda()
+    run = lambda: pli.flash_attention_varlen_paged(q, kd, vd, table.cuda(), lens_t.cuda(), cu, max(q_lens),  # noqa: E731
+                                                   return_lse=True, max_seq_len=max(lens))
+    o0, l0 = run()
+    _poison_unused(kd, vd, table, lens, bs, 0)
+    o1, l1 = run()
+    assert torch.isfinite(o1.float()).all()
+    assert torch.equal(o0, o1) and torch.equal(l0, l1)
+
+    # mixed prefill/decode step over a PagedKVCache whose free pages and page tails are dirty
+    cache = pli.PagedKVCache(num_blocks=96, block_size=bs, num_layers=1, num_heads=Hkv, head_dim=D, dtype=torch.bfloat16)
+    g = torch.Generator(device="cuda").manual_seed(85)
+    plens = {1: 200, 2: 77, 3: 431, 4: 18}
+    for rid, n in plens.items():
+        kn = torch.randn(1, n, Hkv, D, device="cuda", generator=g).bfloat16()
+        vn = torch.randn(1, n, Hkv, D, device="cuda", generator=g).bfloat16()
+        cache.append([rid], kn, vn)
+    qm = torch.randn(150 + 77 + 2, Hq, D, device="cuda", generator=g).bfloat16()
+    step = lambda: pli.mixed_batch_attention(qm, cache, [1, 2], [150, 77], [3, 4])  # noqa: E731
+    m0 = step()
+    used = torch.zeros(96, bs, dtype=torch.bool)
+    for rid, n in plens.items():
+        for t in range(n):
+            used[cache.block_tables[rid].block_indices[t // bs], t % bs] = True
+    cache.k_cache[:, 0][~used.cuda()] = float("nan")
+    cache.v_cache[:, 0][~used.cuda()] = float("-inf")
+    m1 = step()
+    assert torch.isfinite(m1.float()).all() and torch.equal(m0, m1)
+
+
+def test_expanded_zero_stride_views():
+    """Broadcast (zero-stride) K/V such as k.expand(B, ...) or an MQA k[:, :1].expand(-1, H, -1, -1) are read at the
+    right addresses (TMA cannot broadcast: the C layer routes them to the SIMT kernel, the wrapper materialises them
+    first so the tensor-core kernel serves them)."""
+    torch.manual_seed(11)
+    B, Hq, N, D = 3, 8, 200, 128
+    q = torch.randn(B, Hq, N, D, device="cuda", dtype=torch.bfloat16)
+    k1 = torch.randn(1, 2, N, D, device="cuda", dtype=torch.bfloat16)
+    v1 = torch.randn(1, 2, N, D, device="cuda", dtype=torch.bfloat16)
+    ke, ve = k1.expand(B, -1, -1, -1), v1.expand(B, -1, -1, -1)                  # batch stride 0
+    assert ke.stride(0) == 0
+    o = pli.flash_attention_forward(q, ke, ve, causal=True)
+    ref = pli.flash_attention_forward(q, ke.contiguous(), ve.contiguous(), causal=True)
+    assert torch.equal(o, ref)
+    km, vm = k1[:, :1].expand(B, Hq, -1, -1), v1[:, :1].expand(B, Hq, -1, -1)    # MQA: batch and head stride 0
+    o = pli.flash_attention_forward(q, km, vm, causal=False)
+    ro, _ = orc.naive_attention_oracle(q, km, vm)
+    assert (o.float().cpu() - ro).abs().max().item() <= 2e-2
+    # straight through the C ABI (no wrapper normalisation): zero strides select the SIMT kernel, not a wrong tensor map
+    assert _lib.load().pli_prefill_kernel_kind(D, _lib.PLI_BF16, _lib.i64(*q.stride()[:3]), _lib.i64(*ke.stride()[:3]),
+                                               _lib.i64(*ve.stride()[:3]), _lib.i64(*q.stride()[:3]), q.data_ptr(),
+                                               ke.data_ptr(), ve.data_ptr(), q.data_ptr()) == _lib.PLI_KIND_SIMT
+    out = torch.empty_like(q)
+    rc = _lib.load().pli_prefill_fwd(q.data_ptr(), ke.data_ptr(), ve.data_ptr(), out.data_ptr(), None, B, Hq, 2, N, N, D,
+                                     _lib.i64(*q.stride()[:3]), _lib.i64(*ke.stride()[:3]), _lib.i64(*ve.stride()[:3]),
+                                     _lib.i64(*out.stride()[:3]), D ** -0.5, 1, _lib.PLI_BF16,
+                                     torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    assert (out.float() - ref.float()).abs().max().item() <= 2e-2
