@@ -25,6 +25,8 @@ Reference lines each function follows (paths relative to /root/reference):
   paged_decode_oracle         gather_paged + cached_attention_oracle
   combine_splits_oracle       log-sum-exp merge of independent softmax partials
                               (ch06/online_softmax.py:28-53 applied to whole partials)
+  online_softmax_oracle       ch06/online_softmax.py:13-25
+  online_softmax_with_output_oracle   ch06/online_softmax.py:28-53
 """
 from __future__ import annotations
 
@@ -218,6 +220,38 @@ def combine_splits_oracle(o_parts: torch.Tensor, lse_parts: torch.Tensor):
     den = w.sum(dim=0)
     o = (o_parts * w.unsqueeze(-1)).sum(dim=0) / den.unsqueeze(-1)
     return o, m + torch.log(den)
+
+
+def online_softmax_oracle(x: torch.Tensor) -> torch.Tensor:
+    """ch06/online_softmax.py:13-25, statement by statement: one pass with the running (m, d), then normalise."""
+    x = x.detach().to("cpu", torch.float32)
+    n = x.shape[-1]
+    m = x[..., 0].clone()
+    d = torch.ones_like(m)
+    for i in range(1, n):
+        m_new = torch.maximum(m, x[..., i])
+        d = d * torch.exp(m - m_new) + torch.exp(x[..., i] - m_new)
+        m = m_new
+    return torch.exp(x - m.unsqueeze(-1)) / d.unsqueeze(-1)
+
+
+def online_softmax_with_output_oracle(x: torch.Tensor, v: torch.Tensor):
+    """ch06/online_softmax.py:28-53: the recurrence with the running weighted sum; returns (o, d)."""
+    x = x.detach().to("cpu", torch.float32)
+    v = v.detach().to("cpu", torch.float32)
+    n = x.shape[-1]
+    m = x[..., 0].clone()
+    d = torch.ones_like(m)
+    o = v[..., 0, :].clone()
+    for i in range(1, n):
+        m_new = torch.maximum(m, x[..., i])
+        scale_old = torch.exp(m - m_new)
+        scale_new = torch.exp(x[..., i] - m_new)
+        d_new = d * scale_old + scale_new
+        o = (o * d.unsqueeze(-1) * scale_old.unsqueeze(-1) + v[..., i, :] * scale_new.unsqueeze(-1)) / d_new.unsqueeze(-1)
+        m = m_new
+        d = d_new
+    return o, d
 
 
 def seeded_qkv(seed: int, B: int, Hq: int, Hkv: int, Nq: int, Nk: int, D: int, dtype=torch.float32):

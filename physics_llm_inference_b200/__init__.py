@@ -2,7 +2,9 @@
 
 Drop-in surface (same names and call signatures as the reference packages it replaces):
 
-  ch06  flash_attention_forward, FlashAttentionConfig, attention_flops, flash_attention_memory_bytes
+  ch06  flash_attention_forward, FlashAttentionConfig, attention_flops, flash_attention_memory_bytes,
+        online_softmax, online_softmax_with_output, standard_softmax, attention_memory_bytes,
+        attention_arithmetic_intensity          (naive_attention stays on the checker side: oracle/)
   ch02  KVCache, LayerKVCache, create_caches            (+ flash_decode / decode_with_cache)
   ch07  BlockTable, PagedKVCache                        (+ decode_with_paged, prefill_with_paged, kv_append)
 
@@ -18,13 +20,16 @@ from .flash_attention import (FlashAttentionConfig, attention_flops, flash_atten
                               prefill_algorithmic_flops,
                               prefill_kernel_kind)
 from .kv_cache import KVCache, LayerKVCache, create_caches, kv_append
+from .online_softmax import (AttentionMemoryStats, attention_arithmetic_intensity, attention_memory_bytes, online_softmax,
+                             online_softmax_with_output, standard_softmax)
 from .modules import CachedGQA, DecodeGraphRunner, GroupedQueryAttention, TensorParallelGQA
 from .paged_memory import BlockTable, PagedKVCache
 from .sharding import HeadShard, PeerOutput, gather_heads, init_distributed, make_shard, shard_kv_heads
 
 __all__ = [
     "flash_attention_forward", "flash_attention", "flash_attention_paged", "flash_attention_varlen_paged",
-    "FlashAttentionConfig", "attention_flops",
+    "FlashAttentionConfig", "attention_flops", "attention_memory_bytes", "attention_arithmetic_intensity",
+    "AttentionMemoryStats", "online_softmax", "online_softmax_with_output", "standard_softmax",
     "flash_attention_memory_bytes", "prefill_algorithmic_flops", "prefill_kernel_kind",
     "flash_decode", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
     "decode_kernel_kind", "paged_gather", "prefill_with_paged", "mixed_batch_attention",

@@ -753,7 +753,9 @@ extern "C" int pli_decode_splitkv(const void* q, const void* k_store, const void
                         static_cast<cudaStream_t>(stream), nullptr, nullptr, nullptr, nullptr);
 }
 
-// PLI_NO_PDL=1 in the environment launches the combine pass as a plain stream-ordered kernel (A/B measurements)
+// Tuning builds (-DPLI_TUNING=1): PLI_NO_PDL=1 in the environment launches the combine pass as a plain stream-ordered
+// kernel (A/B measurements).  The product build always uses the programmatic dependent launch.
+#if defined(PLI_TUNING) && PLI_TUNING
 static bool pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("PLI_NO_PDL");
@@ -761,6 +763,9 @@ static bool pdl_enabled() {
     }();
     return on;
 }
+#else
+static constexpr bool pdl_enabled() { return true; }
+#endif
 
 static int combine_impl(const void* workspace, void* o, float* lse, int B, int Hq, int D, int num_splits,
                         const int64_t o_strides[2], int dtype, void* stream_, const PeerScatter& peer) {

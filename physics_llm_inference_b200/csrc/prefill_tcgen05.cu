@@ -51,6 +51,12 @@ static_assert(kCorrCols == 0 || kCorrCols == 16 || kCorrCols == 32, "kCorrCols: 
 #ifndef PLI_PROFILE
 #define PLI_PROFILE 0                     // 1: compile the in-kernel timeline / phase counters (tuning builds only)
 #endif
+// PLI_TUNING=1 (build --variant=tuning -DPLI_TUNING=1) compiles the experiment switches: the environment variables
+// PLI_WIDE / PLI_PAIR_MMA / PLI_NO_CLUSTER / PLI_MAX_CTAS, the flag word of pli_debug_prefill_trace and the opt-in wide
+// kernel.  The product library has none of them: its kernel choice depends on the problem alone.
+#ifndef PLI_TUNING
+#define PLI_TUNING (PLI_PROFILE != 0)
+#endif
 constexpr bool kProfile = PLI_PROFILE != 0;
 
 // named barrier ids (0 is __syncthreads)
@@ -447,6 +453,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if constexpr (!kPaged) {
             if (peers.n > 0) peer_buf = (int)((*peers.epoch + 1u) & 1u);
         }
+        int trace_cur = 0;
         uint32_t sf_base = 0;                             // bit t*2+h: parity of s_full[t*2+h]'s first phase in this item
         if (lane == 0) {                                  // first item: O_0 / O_1 are free
             arrive_pv_ok(0);
@@ -467,6 +474,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     mbar_wait_relaxed(&sc_full[bi], (sc_par >> bi) & 1);
 #endif
                     sc_par ^= 1u << bi;
+                    if (wq == 0) trace_event(p, lane, 4, trace_cur, 8, t, s);             // scale factor seen
                     const float alpha = sScale[bi * 128 + row];
                     if constexpr (kCorrCols > 0) {
                         // this warp's share of P_t(s): columns [64 - kCorrCols, 64) of the S buffer (the softmax warp has
@@ -527,6 +535,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     }
                     __syncwarp();
                     if (lane == 0) arrive_pv_ok(bi);
+                    if (wq == 0) trace_event(p, lane, 4, trace_cur, 9, t, s);             // this warp's share of P posted
                 }
             }
             // ---- epilogue: O_t / d -> bf16 -> swizzled smem -> TMA store; LSE ----
@@ -880,6 +889,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     }
 }
 
+#if PLI_TUNING
 // ================================================================================================
 // prefill_wide_kernel (D = 128, CTA pairs, contiguous K/V): ONE 128-row Q tile per CTA, S tiles 128 keys wide in THREE
 // TMEM buffers, CTA-pair MMAs.
@@ -1407,6 +1417,8 @@ prefill_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     if (warp == 0) tmem_dealloc_pair(tmem_base, 512);
 }
 
+#endif  // PLI_TUNING (wide kernel)
+
 // ------------------------------------------------------------------------------------------------
 // UMMA self-test (debug aid, exported as pli_debug_umma_selftest): one 128x128xD tile through the
 // exact descriptor / TMEM paths the prefill kernel uses.  S = A B^T (SS, K-major), then
@@ -1503,37 +1515,29 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (warp == 0) tmem_dealloc(tb, 512);
 }
 
-// CTA-pair MMAs are opt-in (PLI_PAIR_MMA=1 in the environment, or bit 1 of pli_debug_prefill_trace's flags): measured
-// equal to per-CTA MMAs + TMA multicast on the whole chip (1287-1292 vs 1288-1294 TFLOP/s on C2) and 2.5 % slower per SM
-// on part of it, so the simpler protocol stays the default.
-bool wide_env() {                       // PLI_WIDE=1: the one-tile, 128-key-step kernel (prefill_wide_kernel)
-    static const bool on = [] {
-        const char* e = getenv("PLI_WIDE");
-        return e && e[0] == '1';
-    }();
-    return on;
+// Tuning builds only: environment switches for A/B measurements (see PLI_TUNING above).
+#if PLI_TUNING
+bool env_is(const char* name, char value) {
+    const char* e = getenv(name);
+    return e && e[0] == value;
 }
-
-bool pair_mma_env() {
-    static const bool on = [] {
-        const char* e = getenv("PLI_PAIR_MMA");
-        return e && e[0] == '1';
-    }();
-    return on;
+bool wide_env() { static const bool on = env_is("PLI_WIDE", '1'); return on; }               // the one-tile, 128-key-step kernel
+bool pair_mma_off_env() { static const bool off = env_is("PLI_PAIR_MMA", '0'); return off; }  // per-CTA MMAs + TMA multicast
+bool cluster_mode_enabled() { static const bool off = env_is("PLI_NO_CLUSTER", '1'); return !off; }
+int max_ctas_env() {                                    // PLI_MAX_CTAS: experiments on a part of the chip
+    static const int n = [] { const char* e = getenv("PLI_MAX_CTAS"); return e ? atoi(e) : 0; }();
+    return n;
 }
+#else
+constexpr bool cluster_mode_enabled() { return true; }
+constexpr int max_ctas_env() { return 0; }
+#endif
 
-// PLI_NO_CLUSTER=1 in the environment forces the single-CTA kernel (A/B measurements)
-bool cluster_mode_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("PLI_NO_CLUSTER");
-        return !(e && e[0] == '1');
-    }();
-    return on;
-}
-
-unsigned long long* g_trace_buf = nullptr;
+#if PLI_TUNING
+unsigned long long* g_trace_buf = nullptr;   // process-wide, unsynchronised: tuning builds are driven from one thread
 int g_trace_cap = 0;
 int g_debug_flags = 0;
+#endif
 
 int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int H, int B, const int64_t* st,
                 int box_rows = 128) {
@@ -1575,11 +1579,7 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
     int grid = sm_count();
     if (grid <= 0) grid = 148;
-    static const int max_ctas = [] {                    // PLI_MAX_CTAS: tuning experiments on a part of the chip
-        const char* e = getenv("PLI_MAX_CTAS");
-        return e ? atoi(e) : 0;
-    }();
-    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (max_ctas_env() > 0 && grid > max_ctas_env()) grid = max_ctas_env();
     if (grid > p.total_items) grid = p.total_items;
     if (kCluster > 1) grid -= grid % kCluster;          // total_items is a multiple of kCluster in this mode
     cudaLaunchConfig_t cfg = {};
@@ -1599,6 +1599,7 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
     return PLI_OK;
 }
 
+#if PLI_TUNING
 template <bool kBf16, int kGroups>
 int launch_wide(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const CUtensorMap& mo,
                 const PrefillParams& p, cudaStream_t stream, const PeerMaps& peers) {
@@ -1607,11 +1608,7 @@ int launch_wide(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
     int grid = sm_count();
     if (grid <= 0) grid = 148;
-    static const int max_ctas = [] {
-        const char* e = getenv("PLI_MAX_CTAS");
-        return e ? atoi(e) : 0;
-    }();
-    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    if (max_ctas_env() > 0 && grid > max_ctas_env()) grid = max_ctas_env();
     if (grid > p.total_items) grid = p.total_items;
     grid -= grid % 2;                                   // total_items is even (even group size)
     cudaLaunchConfig_t cfg = {};
@@ -1630,6 +1627,8 @@ int launch_wide(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     count_launch();
     return PLI_OK;
 }
+
+#endif
 
 // 5-D map over a paged pool (num_pages, layers, page_size, Hkv, D): dims fastest first d, head, slot, layer, page
 int make_pool_map(CUtensorMap* map, const void* base, int dtype, int D, int Hkv, int page_size, int layers, int64_t pages,
@@ -1658,9 +1657,15 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
     int grid = sm_count() > 0 ? sm_count() : 148;
     p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);   // in 128- or 256-row slots
     if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
+#if PLI_TUNING
     p.trace = g_trace_buf;
     p.trace_cap = g_trace_cap;
     p.debug_flags = g_debug_flags;
+#else
+    p.trace = nullptr;
+    p.trace_cap = 0;
+    p.debug_flags = 0;
+#endif
     p.table = nullptr;
     p.seq_lens = nullptr;
     p.table_stride = p.page_size = p.page_shift = p.layer = p.box_rows = 0;
@@ -1754,9 +1759,14 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     // (even, odd) items share their K/V when the per-group item count is even: group size divisible by 4 with
     // head-pair items (group size odd -> row-pair items of single heads -> never)
     const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
-    // pair MMAs (D = 128): each CTA loads 32-key boxes of K and full-height, 64-column boxes of V (its half of B)
-    const bool pair_mma = pairs && D == 128 && (pair_mma_env() || (g_debug_flags & 2));
-    // one Q tile per CTA, 128-key S tiles, pair MMAs (any even group size): opt-in
+    // CTA-pair MMAs (D = 128, cta_group::2): each CTA loads 32-key boxes of K and full-height, 64-column boxes of V (its
+    // half of B).  The default whenever a pair of CTAs shares its K/V: with the correction warps sharing the softmax
+    // work the tensor side matters again, and the pair instructions run the kernel's MMA sequence in 1183 instead of
+    // 1283 cycles: measured +2 % on C2 (1298-1306 against 1274-1283 TFLOP/s, same box), bit-identical.
+    bool pair_mma = pairs && D == 128;
+#if PLI_TUNING
+    if (pair_mma_off_env() || (g_debug_flags & 64)) pair_mma = false;      // flags bit 6: per-CTA MMAs + TMA multicast
+    // one Q tile per CTA, 128-key S tiles, pair MMAs (any even group size): opt-in experiment
     const bool wide = D == 128 && (Hq / Hkv) % 2 == 0 && cluster_mode_enabled() && (wide_env() || (g_debug_flags & 4));
     if (wide) {
         if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, kHN))) return rc;
@@ -1788,6 +1798,7 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
         return dtype == PLI_BF16 ? launch_wide<true, 3>(mq, mk, mv, mo, p, stream, pm)
                                  : launch_wide<false, 3>(mq, mk, mv, mo, p, stream, pm);
     }
+#endif  // PLI_TUNING
     if ((rc = make_map_4d(&mk, k, dtype, D, Nk, Hkv, B, ks, pair_mma ? kHN / 2 : pairs ? kHN : kBN))) return rc;
     if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pair_mma ? kBN : pairs ? kHN : kBN))) return rc;
     if (peer != nullptr) mo = pm.maps[0][0];
@@ -1825,13 +1836,21 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
 using namespace pli;
 
 // Debug aid: record CTA 0's pipeline timeline of the next prefill launches into `buf` (device memory of
-// 4 regions x capacity x 16 bytes, zeroed by the caller); buf = NULL switches it off.  flags bit 1: CTA-pair MMAs
+// 5 regions x capacity x 16 bytes, zeroed by the caller); buf = NULL switches it off.  flags (tuning builds): bit 2 wide kernel (bit 5: with two softmax
+// warpgroups), bit 6 per-CTA MMAs instead of CTA-pair MMAs; formerly bit 1: CTA-pair MMAs
 // (tcgen05.mma.cta_group::2) for the following launches (tuning / tests).
 extern "C" int pli_debug_prefill_trace(void* buf, int capacity, int flags) {
+#if PLI_TUNING
     g_trace_buf = static_cast<unsigned long long*>(buf);
     g_trace_cap = buf ? capacity : 0;
     g_debug_flags = flags;
     return PLI_OK;
+#else
+    (void)buf; (void)capacity;
+    if (flags == 0) return PLI_OK;           // "switch everything off" is always satisfiable
+    return set_error(PLI_ERR_UNSUPPORTED, "this is the product build: kernel-selection flags and the timeline exist only in "
+                                          "tuning builds (python -m physics_llm_inference_b200.build --variant=tuning -DPLI_TUNING=1)");
+#endif
 }
 
 // Debug aid (not part of the reference-facing surface): a (128 x D), b (128 x D), c (128 x D) row-major

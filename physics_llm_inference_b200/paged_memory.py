@@ -126,6 +126,63 @@ class PagedKVCache:
         self.block_tables[child_id] = table
         return table
 
+    def kv_indices(self, request_id: int) -> list[int]:
+        """Flat slot address `page * block_size + slot` of every cached token of a request, in token order: the
+        per-token `kv_indices` a `RadixCache.insert(token_ids, kv_indices)` (ch07/radix_cache.py:20-70) records."""
+        if request_id not in self.block_tables:
+            raise KeyError(f"Request {request_id} not found")
+        table = self.block_tables[request_id]
+        bs = self.block_size
+        return [table.block_indices[t // bs] * bs + t % bs for t in range(table.num_tokens)]
+
+    def share_prefix(self, child_id: int, matched: int, kv_indices: list[int]) -> BlockTable:
+        """Start request `child_id` from a radix-cache hit: `(matched, kv_indices)` exactly as
+        `RadixCache.match_prefix(token_ids)` returns them (ch07/radix_cache.py:72-103: the number of matched tokens and
+        one KV slot address per matched token, here `page * block_size + slot` as produced by `kv_indices()`).
+
+        The per-token addresses are turned into page-granular sharing: every run of `block_size` tokens that occupies
+        one whole physical page in order is ALIASED (the child's block table points at the same page, ref-counted —
+        nothing is copied or recomputed); the remainder (a partly filled last page, or addresses that are not
+        page-aligned) is gathered into a fresh page so the child can append behind it.  Returns the child's table with
+        `num_tokens = min(matched, len(kv_indices))`; the caller computes K/V only for the tokens after it."""
+        if child_id in self.block_tables:
+            raise ValueError(f"Request {child_id} already has a block table")
+        bs = self.block_size
+        n = min(int(matched), len(kv_indices))
+        if n < 0:
+            raise ValueError("matched must be non-negative")
+        chunks = []                                                # (alias page | None, [slot addresses])
+        for a in range(0, n, bs):
+            slots = [int(x) for x in kv_indices[a:min(a + bs, n)]]
+            page = slots[0] // bs
+            whole = len(slots) == bs and all(sl == page * bs + i for i, sl in enumerate(slots))
+            for sl in slots:
+                pg = sl // bs
+                if not 0 <= pg < self.num_blocks or pg in self.free_blocks:
+                    raise RuntimeError(f"kv index {sl} points at page {pg}, which is not allocated (stale prefix entry)")
+            chunks.append((page if whole else None, slots))
+        fresh = sum(1 for pg, _ in chunks if pg is None)
+        if fresh > len(self.free_blocks):
+            raise RuntimeError(f"Not enough free blocks: need {fresh}, have {len(self.free_blocks)}")
+        pages = []
+        for pg, slots in chunks:
+            if pg is not None:
+                self.shared_refs[pg] = self.shared_refs.get(pg, 1) + 1
+                pages.append(pg)
+                continue
+            new_page = self.free_blocks.pop()
+            if self.k_cache is not None:
+                dev = self.k_cache.device
+                src_pages = torch.tensor([sl // bs for sl in slots], dtype=torch.long, device=dev)
+                src_slots = torch.tensor([sl % bs for sl in slots], dtype=torch.long, device=dev)
+                # (n_tok, layers, heads, dim) -> the first n_tok slots of the new page, every layer
+                self.k_cache[new_page, :, :len(slots)] = self.k_cache[src_pages, :, src_slots].transpose(0, 1)
+                self.v_cache[new_page, :, :len(slots)] = self.v_cache[src_pages, :, src_slots].transpose(0, 1)
+            pages.append(new_page)
+        table = BlockTable(request_id=child_id, block_indices=pages, num_tokens=n)
+        self.block_tables[child_id] = table
+        return table
+
     def get_num_free_blocks(self) -> int:
         return len(self.free_blocks)
 

@@ -55,3 +55,41 @@ def test_decode_random_shapes():
         eo = (o.float().cpu() - ro).abs().max().item()
         el = (lse.cpu() - rlse[:, :, 0]).abs().max().item()
         assert eo <= 2e-2 and el <= 1e-3, (case, B, Hkv, G, D, bs, lens, dtype, splits, layer, eo, el)
+
+
+def test_online_softmax_row_kernels(golden_dir):
+    """a3: `online_softmax` / `online_softmax_with_output` (ch06/online_softmax.py:13-53) on the GPU against the
+    reference's own outputs (ch06_online.npz, r2_ch06_surface.npz; the reference's tolerances: 1e-4 / 1e-3,
+    ch06/test_ch06.py:84-120) and against the oracle on other shapes and dtypes."""
+    import os
+
+    import numpy as np
+    g = np.load(os.path.join(golden_dir, "ch06_online.npz"))
+    s = np.load(os.path.join(golden_dir, "r2_ch06_surface.npz"))
+    x, v = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["v"]).cuda()
+    sm = pli.online_softmax(x)
+    assert sm.shape == x.shape and sm.dtype == x.dtype
+    assert (sm.cpu() - torch.from_numpy(s["online"])).abs().max().item() <= 1e-4
+    assert (sm.sum(-1) - 1).abs().max().item() <= 1e-5
+    assert (pli.standard_softmax(x).cpu() - torch.from_numpy(s["standard"])).abs().max().item() <= 1e-6
+    o, d = pli.online_softmax_with_output(x, v)
+    assert o.shape == (3, 5, 8) and d.shape == (3, 5)
+    assert (o.cpu() - torch.from_numpy(g["o"])).abs().max().item() <= 1e-3
+    assert ((d.cpu() - torch.from_numpy(g["d"])) / torch.from_numpy(g["d"])).abs().max().item() <= 1e-5
+    rng = torch.Generator().manual_seed(17)
+    for shape, dv, dtype, tol in [((7,), 3, torch.float32, 1e-4), ((2, 3, 1), 5, torch.float32, 1e-4),
+                                  ((5, 1000), 130, torch.float32, 1e-4), ((4, 33, 77), 64, torch.bfloat16, 2e-2),
+                                  ((300, 17), 256, torch.float16, 2e-2)]:
+        xs = (torch.randn(*shape, generator=rng) * 4).to(dtype)
+        vs = torch.randn(*shape, dv, generator=rng).to(dtype)
+        got = pli.online_softmax(xs.cuda())
+        assert (got.float().cpu() - orc.online_softmax_oracle(xs)).abs().max().item() <= tol
+        go, gd = pli.online_softmax_with_output(xs.cuda(), vs.cuda())
+        ro, rd = orc.online_softmax_with_output_oracle(xs, vs)
+        assert go.dtype == dtype and gd.dtype == dtype
+        assert (go.float().cpu() - ro).abs().max().item() <= max(tol, 1e-3)
+        assert ((gd.float().cpu() - rd) / rd).abs().max().item() <= (1e-5 if dtype == torch.float32 else 1e-2)
+    # a strided view (last dim contiguous, rows not)
+    big = torch.randn(6, 50, device="cuda")
+    view = big[:, 10:30]
+    assert (pli.online_softmax(view) - torch.softmax(view, -1)).abs().max().item() <= 1e-6

@@ -111,3 +111,84 @@ def test_tensor_parallel_gqa_shards_sum_to_the_full_block(world):
     assert (sum(parts) - ref).abs().max().item() <= tol
     with pytest.raises(ValueError):
         pli.TensorParallelGQA(Hq * D, Hq, Hkv, world_size=3, rank=0)
+
+
+def test_cached_generate_on_the_kernels_gives_the_reference_tokens(golden_dir):
+    """F4 tail: the reference's `cached_generate` loop (ch02/cached_generation.py:208-274) over a model whose attention
+    block is this package's `CachedGQA` (prefill on the causal kernel, every decode step on the split-KV kernel, K/V
+    appended by pli_kv_append), fp32, greedy (temperature 1e-6): token ids identical to what the UNMODIFIED reference
+    model generated on the CPU (tests/golden/r2_ch02_generate.npz, oracle/make_golden_r2.py)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from tiny_model import TinyCachedModel, cached_generate
+    g = np.load(os.path.join(golden_dir, "r2_ch02_generate.npz"))
+    vocab, hidden, layers, heads, kv_heads, inter = [int(x) for x in g["cfg"]]
+    seed, batch, prompt_len, n_new = [int(x) for x in g["meta"]]
+    torch.manual_seed(seed)
+    model = TinyCachedModel(pli.CachedGQA, vocab, hidden, layers, heads, kv_heads, inter)
+    wsum = np.array([float(p.double().sum()) for p in model.parameters()] +
+                    [float((p.double() ** 2).sum()) for p in model.parameters()])
+    assert np.allclose(wsum, g["wsum"], rtol=0, atol=1e-9), "seeded weights differ from the reference model's"
+    model = model.cuda()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    prompt = torch.from_numpy(g["prompt"]).cuda()
+    make = lambda b, n: pli.create_caches(layers, b, n, kv_heads, hidden // heads, "cuda", torch.float32)  # noqa: E731
+    pli.reset_launch_count()
+    tokens, logits = cached_generate(model, prompt, n_new, make, temperature=1e-6)
+    assert pli.launch_count() >= layers * (2 * n_new)            # an append and an attention launch per layer per step
+    assert torch.equal(tokens.cpu(), torch.from_numpy(g["tokens"]))
+    assert (logits[:, -1, :].cpu() - torch.from_numpy(g["last_logits"])).abs().max().item() <= 1e-3
+
+
+def test_radix_hit_shares_pages_and_decodes_like_an_unshared_request(golden_dir):
+    """F3: `(matched, kv_indices)` as the reference's RadixCache.match_prefix returned them (tests/golden/
+    r2_ch07_radix.json) -> PagedKVCache.share_prefix: whole pages aliased, the partly filled page copied; the child then
+    appends its own tokens and decodes bit-identically to a request that holds all of its tokens in private pages."""
+    import json
+    with open(os.path.join(golden_dir, "r2_ch07_radix.json")) as f:
+        r = json.load(f)
+    bs, Hkv, Hq, D, layers = r["block_size"], 2, 8, 128, 2
+    cache = pli.PagedKVCache(num_blocks=32, block_size=bs, num_layers=layers, num_heads=Hkv, head_dim=D, dtype=torch.bfloat16)
+    # request A lives in the pages the scenario names
+    for pg in r["pages_a"]:
+        cache.free_blocks.remove(pg)
+    cache.block_tables[1] = pli.BlockTable(request_id=1, block_indices=list(r["pages_a"]), num_tokens=0)
+    g = torch.Generator(device="cuda").manual_seed(91)
+    n_a = len(r["a_tokens"])
+    ka = torch.randn(layers, 1, n_a, Hkv, D, device="cuda", generator=g).bfloat16()
+    va = torch.randn(layers, 1, n_a, Hkv, D, device="cuda", generator=g).bfloat16()
+    cache.block_tables[1].num_tokens = n_a
+    for layer in range(layers):
+        cache.append([1], ka[layer], va[layer], layer=layer, extend=False)
+    assert cache.kv_indices(1) == r["a_kv"]
+    hit = r["queries"]["b_shares_53"]
+    matched, n_b = hit["matched"], len(hit["tokens"])
+    free_before = cache.get_num_free_blocks()
+    tb = cache.share_prefix(2, matched, hit["kv_indices"])
+    assert tb.num_tokens == 53 and tb.block_indices[:3] == r["pages_a"][:3] and tb.block_indices[3] not in r["pages_a"]
+    assert cache.get_num_free_blocks() == free_before - 1
+    # B's own tokens after the shared prefix, and the same request built privately (prefix K/V recomputed = copied)
+    kb = torch.randn(layers, 1, n_b - matched, Hkv, D, device="cuda", generator=g).bfloat16()
+    vb = torch.randn(layers, 1, n_b - matched, Hkv, D, device="cuda", generator=g).bfloat16()
+    for layer in range(layers):
+        cache.append([2], kb[layer], vb[layer], layer=layer, extend=(layer == 0))
+        cache.append([3], torch.cat([ka[layer][:, :matched], kb[layer]], 1), torch.cat([va[layer][:, :matched], vb[layer]], 1),
+                     layer=layer, extend=(layer == 0))
+    q = torch.randn(1, Hq, 1, D, device="cuda", generator=g).bfloat16()
+    for layer in range(layers):
+        o_shared = pli.decode_with_paged(q, cache, [2], layer=layer)
+        o_private = pli.decode_with_paged(q, cache, [3], layer=layer)
+        assert torch.equal(o_shared, o_private)
+        ro, _ = orc.cached_attention_oracle(q, torch.cat([ka[layer][:, :matched], kb[layer]], 1),
+                                            torch.cat([va[layer][:, :matched], vb[layer]], 1), n_b)
+        assert (o_shared.float().cpu() - ro).abs().max().item() <= 2e-2
+    # A is untouched by B's appends (B wrote into its private copy of the partly shared page), and freeing A keeps the
+    # aliased pages alive for B
+    o_a = pli.decode_with_paged(q, cache, [1], layer=0)
+    ro, _ = orc.cached_attention_oracle(q, ka[0], va[0], n_a)
+    assert (o_a.float().cpu() - ro).abs().max().item() <= 2e-2
+    cache.free_blocks_for_request(1)
+    assert all(pg not in cache.free_blocks for pg in r["pages_a"][:3]) and all(pg in cache.free_blocks for pg in r["pages_a"][3:])
+    assert torch.equal(pli.decode_with_paged(q, cache, [2], layer=1), pli.decode_with_paged(q, cache, [3], layer=1))
+    cache.free_blocks_for_request(2)
+    assert all(pg in cache.free_blocks for pg in r["pages_a"])

@@ -182,3 +182,65 @@ def test_prefix_sharing_refcounts():
         c.fork_request(9, 4)
     with pytest.raises(ValueError):
         c.allocate_blocks(5, 10) and c.fork_request(5, 6, 11)
+
+
+def test_ch06_accounting_surface_matches_reference(golden_dir):
+    """attention_memory_bytes / AttentionMemoryStats (ch06/attention_memory.py:6-16,36-61) and
+    attention_arithmetic_intensity (:78-86): same integers as the unmodified reference (r2_ch06_surface.npz)."""
+    g = np.load(os.path.join(golden_dir, "r2_ch06_surface.npz"))
+    for cfg, ref, mb in zip(g["mem_cfgs"], g["mem"], g["mem_total_mb"]):
+        s = pli.attention_memory_bytes(*[int(x) for x in cfg])
+        assert isinstance(s, pli.AttentionMemoryStats)
+        got = [s.batch_size, s.num_heads, s.seq_len, s.head_dim, s.qk_bytes, s.softmax_bytes, s.output_bytes, s.total_bytes]
+        assert got == [int(x) for x in ref]
+        assert s.total_mb == float(mb)
+    s = pli.attention_memory_bytes(batch_size=1, num_heads=8, seq_len=512, head_dim=64)      # default dtype_bytes = 2
+    assert s.qk_bytes == 1 * 8 * 512 * 512 * 2
+    for cfg, ref in zip(g["ai_cfgs"], g["ai"]):
+        assert pli.attention_arithmetic_intensity(int(cfg[0]), int(cfg[1])) == float(ref)
+    with pytest.raises(RuntimeError):
+        pli.online_softmax(torch.randn(4, 8))                      # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        pli.online_softmax_with_output(torch.randn(4, 8), torch.randn(4, 8, 2))
+
+
+def test_share_prefix_from_a_radix_hit_is_page_granular(golden_dir):
+    """F3 bookkeeping on the host (no pools needed): `(matched, kv_indices)` of the reference's RadixCache.match_prefix
+    (r2_ch07_radix.json) -> aliased whole pages + one fresh page for the partly filled remainder, ref-counted."""
+    import json
+    with open(os.path.join(golden_dir, "r2_ch07_radix.json")) as f:
+        r = json.load(f)
+    bs = r["block_size"]
+    cache = pli.PagedKVCache(num_blocks=32, block_size=bs, num_layers=1, num_heads=2, head_dim=8, device="cpu")
+    for pg in r["pages_a"]:
+        cache.free_blocks.remove(pg)
+    cache.block_tables[1] = pli.BlockTable(request_id=1, block_indices=list(r["pages_a"]), num_tokens=len(r["a_tokens"]))
+    assert cache.kv_indices(1) == r["a_kv"]
+    assert r["inserted_a"] == len(r["a_tokens"])
+    free0 = cache.get_num_free_blocks()
+    b = r["queries"]["b_shares_53"]
+    tb = cache.share_prefix(2, b["matched"], b["kv_indices"])
+    assert tb.num_tokens == 53 and tb.block_indices[:3] == r["pages_a"][:3] and len(tb.block_indices) == 4
+    assert cache.get_num_free_blocks() == free0 - 1 and all(cache.shared_refs[p] == 2 for p in r["pages_a"][:3])
+    c = r["queries"]["c_shares_32"]
+    tc = cache.share_prefix(3, c["matched"], c["kv_indices"])
+    assert tc.num_tokens == 32 and tc.block_indices == r["pages_a"][:2]          # page-aligned hit: nothing copied
+    assert cache.get_num_free_blocks() == free0 - 1 and cache.shared_refs[r["pages_a"][0]] == 3
+    d = r["queries"]["d_shares_0"]
+    td = cache.share_prefix(4, d["matched"], d["kv_indices"])
+    assert td.num_tokens == 0 and td.block_indices == []
+    e = r["queries"]["e_whole"]
+    te = cache.share_prefix(5, e["matched"], e["kv_indices"])
+    assert te.num_tokens == 70 and te.block_indices[:4] == r["pages_a"][:4] and te.block_indices[4] != r["pages_a"][4]
+    # the child grows like any request (ch07/paged_memory.py:76-98) and frees without releasing shared pages
+    cache.extend_blocks(2, 20)
+    assert cache.block_tables[2].num_tokens == 73 and cache.block_tables[2].num_blocks() == 5
+    with pytest.raises(ValueError):
+        cache.share_prefix(2, 1, [0])                              # id in use
+    with pytest.raises(RuntimeError):
+        cache.share_prefix(9, 16, list(range(31 * bs, 32 * bs)) if 31 in cache.free_blocks else [999999] * 16)   # stale
+    for rid in (1, 3, 4, 5):
+        cache.free_blocks_for_request(rid)
+    assert all(p not in cache.free_blocks for p in r["pages_a"][:3])             # still referenced by request 2
+    cache.free_blocks_for_request(2)
+    assert cache.get_num_free_blocks() == 32 and not cache.shared_refs

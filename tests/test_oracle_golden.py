@@ -140,3 +140,15 @@ def test_split_combine_is_exact():
     o, l = orc.combine_splits_oracle(torch.stack(parts), torch.stack(lses))
     assert (o - full).abs().max().item() <= 2e-6
     assert (l - lse).abs().max().item() <= 2e-6
+
+
+def test_ch06_online_softmax_functions_bit_equal(golden_dir):
+    """oracle restatements of ch06/online_softmax.py:13-53 == the reference's outputs (r2_ch06_surface.npz / ch06_online.npz)."""
+    g = _load(golden_dir, "ch06_online.npz")
+    s = _load(golden_dir, "r2_ch06_surface.npz")
+    x, v = torch.from_numpy(g["x"]), torch.from_numpy(g["v"])
+    assert torch.equal(orc.online_softmax_oracle(x), torch.from_numpy(s["online"]))
+    o, d = orc.online_softmax_with_output_oracle(x, v)
+    assert torch.equal(o, torch.from_numpy(g["o"])) and torch.equal(d, torch.from_numpy(g["d"]))
+    # the reference's own property (ch06/test_ch06.py:84-88): online == standard to 1e-4
+    assert (torch.from_numpy(s["online"]) - torch.from_numpy(s["standard"])).abs().max().item() <= 1e-4

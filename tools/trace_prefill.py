@@ -14,7 +14,7 @@ lib = _lib.load()
 for _ in range(2):
     pli.flash_attention_forward(q, k, v, causal=True)
 cap = 20000
-buf = torch.zeros(4 * cap * 2, dtype=torch.int64, device="cuda")
+buf = torch.zeros(5 * cap * 2, dtype=torch.int64, device="cuda")
 lib.pli_debug_prefill_trace(buf.data_ptr(), cap, flags)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 # argv[2] = number of untraced launches issued back to back in front of the traced one (the traced launch then
@@ -33,13 +33,13 @@ lib.pli_debug_prefill_trace(None, 0, 0)
 ms = e0.elapsed_time(e1)
 print(f"flags={flags} kernel {ms:.3f} ms (with tracing), after {lead} back-to-back launches")
 h = buf.cpu().tolist()
-recs = [(h[2 * i + 1], h[2 * i] & 0xFF, (h[2 * i] >> 8) & 0xFF, (h[2 * i] >> 16) & 0xFFFF) for i in range(4 * cap) if h[2 * i] >> 40]
+recs = [(h[2 * i + 1], h[2 * i] & 0xFF, (h[2 * i] >> 8) & 0xFF, (h[2 * i] >> 16) & 0xFFFF) for i in range(5 * cap) if h[2 * i] >> 40]
 recs.sort()
 t0 = recs[0][0]
 span = recs[-1][0] - t0
 print(f"CTA 0: {span} SM cycles between its first and last event = {span / ms / 1e3:.0f} MHz if they span the kernel "
       f"(the SM clock the kernel actually ran at; nvidia-smi's samples are too coarse to see it)")
-names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "S_in_registers", 7: "exp_done"}
+names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "S_in_registers", 7: "exp_done", 8: "corr_start", 9: "corr_posted"}
 print("first item: events of half-steps 40..44 (regions: softmax tile 0/1, MMA warp of tile 0/1)")
 for clk, ev, t, j in recs:
     if 40 <= j <= 44 and clk - t0 < 800000:
@@ -70,5 +70,9 @@ for t in (0, 1):
     issue = [ev[(t, j)][5] - ev[(t, j)][4] for j in js if 5 in ev[(t, j)] and 4 in ev[(t, j)]]
     turn = [ev[(t, j + 1)][1] - ev[(t, j)][5] for j in js if (t, j + 1) in ev and 1 in ev[(t, j + 1)] and 5 in ev[(t, j)]]
     period = [ev[(t, j + 1)][1] - ev[(t, j)][1] for j in js if (t, j + 1) in ev and 1 in ev[(t, j + 1)] and 1 in ev[(t, j)]]
+    cw = [ev[(t, j)][9] - ev[(t, j)][8] for j in js if 9 in ev[(t, j)] and 8 in ev[(t, j)]]
+    clag = [ev[(t, j)][9] - ev[(t, j)][3] for j in js if 9 in ev[(t, j)] and 3 in ev[(t, j)]]
+    cst = [ev[(t, j)][8] - ev[(t, j)][2] for j in js if 8 in ev[(t, j)] and 2 in ev[(t, j)]]
+    print(f"tile{t}: correction warp: scale posted -> seen {avg(cst):.0f} | its share of P {avg(cw):.0f} | posted relative to the softmax warp's P_posted {avg(clag):+.0f}")
     print(f"tile{t}: softmax(S_ready->P_posted) {avg(soft):.0f}  of which ld+max {avg(mx):.0f} | P_posted->mma_inputs_ready {avg(p2go):.0f} | "
           f"issue {avg(issue):.0f} | issued->next S_ready {avg(turn):.0f} | period {avg(period):.0f} cycles")
