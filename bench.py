@@ -1,29 +1,37 @@
 """bench.py — the hot path's headline benchmark (BASELINE.json: prefill attn TFLOP/s & paged-decode
-KV GB/s, % of roofline).
+KV GB/s at 1/2/4/8 B200, % of roofline).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the workload is
-BASELINE config 2 (C2): Llama-3-8B-shaped causal GQA prefill, B4, 32 q / 8 kv heads, D128, N8192,
-bf16 — one `flash_attention_forward` call = one tcgen05 kernel launch.  `value` is whole-job TFLOP/s
-with q/k/v resident in HBM (algorithmic FLOPs 4*B*Hq*N^2*D/2); `e2e` is the same
-metric through the public API with HOST (pinned) buffers, H2D of q,k,v and D2H of O inside the timed
-region.  The second half of the metric, paged decode (C3: B64, ctx 4096, 16-token pages), is timed in
-the same run and reported under `decode` with its own HBM roofline.
+A "step" is one pass of the hot path over one batch of synthetic input.
 
-N>1 (torchrun, one rank per GPU): attention has no exchange step, so units (batch x KV-head groups)
-are sharded with no data-path collective: each rank runs one C2-sized shard (global batch 4N) —
-`"scaling": "weak"` — and the time is the max over ranks.
+N = 1   BASELINE config 2 (C2): Llama-3-8B-shaped causal GQA prefill, B4, 32 q / 8 kv heads, D128, N8192, bf16 —
+        one `flash_attention_forward` call = one tcgen05 kernel launch.  `value` is TFLOP/s with q/k/v resident in HBM
+        (algorithmic FLOPs 4*B*Hq*N^2*D/2); `e2e` is the same metric through the public API with HOST
+        (pinned) buffers, H2D of q,k,v and D2H of O inside the timed region.  The second half of the metric, paged
+        decode (C3: B64, ctx 4096, 16-token pages), is timed in the same run under `decode` with its own HBM roofline;
+        `shapes` carries the off-headline prefill shapes, each with its own roofline fraction.
+N > 1   (torchrun, one rank per GPU) the partitioned workload north_star describes, BASELINE config 4 (C4): ONE causal
+        prefill of N = 65 536 (B1, 32 q / 8 kv heads, 35.18 TFLOP), its KV-head groups sharded over the ranks, every
+        rank's output tiles TMA-stored into ALL ranks' full output over NVLink by the kernel itself (fused all-gather:
+        `flash_attention_forward(..., peer_out=)`), so every rank ends the step holding the full (1, 32, N, D) tensor.
+        `"scaling": "strong"`: total work is fixed, `value` = 35.18 TFLOP / max-over-ranks step time.  Each step's fused
+        output is checked bit-for-bit against the NCCL all-gather of the plain kernel's output and row-sampled against
+        the oracle (`parity`).  Weak-scaling C2 and the C5 decode sweep (B256, ctx 1k-32k, fused vs NCCL gather, with
+        their own parity keys) ride along under `weak_c2` / `strong_scaling_configs`.
 
 `--impl reference`: the reference's CPU implementation of the same path (the oracle port of
-ch06.flash_attention_forward + ch01 mask/GQA; /root/reference does not exist on the GPU box), all
-host threads, on a bounded sample of the same workload.
+ch06.flash_attention_forward + ch01 mask/GQA; /root/reference does not exist on the GPU box) on the box's host cores.
+The GPU arm's `cpu_baseline` leg and this arm run THE SAME helper (`cpu_prefill_child`) in a fresh child process with
+the same thread policy, so the two agree by construction.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -36,10 +44,8 @@ METRIC = "prefill_attn_tflops"
 UNIT = "TFLOP/s"
 C2 = dict(B=4, Hq=32, Hkv=8, N=8192, D=128)
 C3 = dict(B=64, Hq=32, Hkv=8, L=4096, D=128, bs=16)
-# bounded CPU sample of C2: one of the four batch rows (all 32 q / 8 kv heads), full N, causal
-CPU_SAMPLE = dict(B=1, Hq=32, Hkv=8, N=8192, D=128)
+C4 = dict(B=1, Hq=32, Hkv=8, N=65536, D=128)
 CPU_DECODE_SAMPLE = dict(B=16, Hq=32, Hkv=8, L=4096, D=128, bs=16)
-
 
 _JSON_FD = None
 
@@ -82,11 +88,25 @@ def load_traffic(key: str):
         return None
 
 
-def config_dict(n_gpus: int):
+def c2_config(n_gpus: int):
     return {"workload": "C2: causal GQA prefill, 32q/8kv heads, D128, N8192, batch 4 per GPU, bf16",
             "global_batch": C2["B"] * n_gpus, "seq_len": C2["N"], "heads": f"{C2['Hq']}q/{C2['Hkv']}kv",
-            "head_dim": C2["D"], "causal": True, "parallelism": f"batch x kv-head shard x{n_gpus}, no collective",
+            "head_dim": C2["D"], "causal": True,
+            "parallelism": "one GPU" if n_gpus == 1 else f"batch x kv-head shard x{n_gpus}, no collective",
             "l2_policy": "inputs larger than L2 (640 MB of q/k/v/o per step vs 126 MB L2)"}
+
+
+def c4_config(n_gpus: int):
+    return {"workload": "C4: ONE causal GQA prefill N65536, B1, 32q/8kv heads, D128, bf16 (35.18 TFLOP), KV-head groups "
+                        f"sharded over {n_gpus} GPUs, output all-gather fused into the kernel (TMA stores to every rank over NVLink)",
+            "global_batch": 1, "seq_len": C4["N"], "heads": f"{C4['Hq']}q/{C4['Hkv']}kv", "head_dim": C4["D"], "causal": True,
+            "parallelism": f"kv-head groups x{n_gpus} ({C4['Hkv'] // n_gpus} per GPU) + fused NVLink all-gather of O",
+            "l2_policy": "inputs and the 512 MiB output are larger than L2"}
+
+
+def decode_bytes(B, Hq, Hkv, L, D, bs, elt=2):
+    """Algorithmic bytes of one decode step (SURVEY.md 8(d)): K and V once, q and o, the block table."""
+    return 2 * B * L * Hkv * D * elt + 2 * B * Hq * D * elt + 4 * B * ((L + bs - 1) // bs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -151,127 +171,301 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port), shared by the cpu_baseline key and --impl reference
+# CPU baseline: ONE helper, run in a fresh child process by both the `cpu_baseline` leg and `--impl reference`
 # ------------------------------------------------------------------------------------------------
-def cpu_prefill_sample(reps: int = 1):
-    """Oracle restatement of ch06 (+ch01 causal mask and GQA map) on a bounded sample of C2."""
+def host_threads() -> dict:
+    """Thread policy of the CPU arm: every host core this process may really use = min(CPU affinity, cgroup CPU quota,
+    physical cores).  `os.cpu_count()` alone can exceed the container's quota (round 1: the reference arm asked for
+    os.cpu_count() threads and ran 2.65x slower than the same code at torch's default)."""
+    affinity = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+            if q != "max":
+                quota = max(1, math.ceil(int(q) / int(p)))
+    except Exception:  # noqa: BLE001
+        pass
+    physical = None
+    try:
+        import psutil
+        physical = psutil.cpu_count(logical=False)
+    except Exception:  # noqa: BLE001
+        pass
+    n = affinity
+    if quota:
+        n = min(n, quota)
+    if physical:
+        n = min(n, physical)
+    return {"threads": max(1, n), "os_cpu_count": os.cpu_count(), "affinity": affinity, "cgroup_quota": quota,
+            "physical_cores": physical}
+
+
+def cpu_child_main(kind: str, passes: int):
+    """Child process: oracle restatement of the reference's CPU path on the C2 step, `passes` timed passes after one
+    warm-up pass.  Prints one JSON line."""
     import torch
 
     from oracle import attention_oracle as orc
-    s = CPU_SAMPLE
-    q, k, v = orc.seeded_qkv(0xC0FFEE + 2, s["B"], s["Hq"], s["Hkv"], s["N"], s["N"], s["D"])
-    best = float("inf")
-    for _ in range(reps):
+    pol = host_threads()
+    torch.set_num_threads(pol["threads"])
+    if kind == "prefill":
+        s = C2
+        q, k, v = orc.seeded_qkv(0xC0FFEE + 2, s["B"], s["Hq"], s["Hkv"], s["N"], s["N"], s["D"])
+        work = 4.0 * s["B"] * s["Hq"] * s["N"] * s["N"] * s["D"] / 2
+        run = lambda: orc.flash_attention_oracle(q, k, v, causal=True, skip_masked_blocks=True)  # noqa: E731
+        sample = (f"oracle port of ch06.flash_attention_forward (+ch01 causal mask, GQA map), fp32, on the WHOLE C2 step "
+                  f"(B{s['B']} x {s['Hq']}q/{s['Hkv']}kv heads x N{s['N']} x D{s['D']})")
+    else:
+        s = CPU_DECODE_SAMPLE
+        qd, kp, vp, table, lens = orc.seeded_paged(0xC0FFEE + 3, s["B"], s["Hq"], s["Hkv"], s["D"], s["bs"], [s["L"]] * s["B"])
+        work = float(decode_bytes(s["B"], s["Hq"], s["Hkv"], s["L"], s["D"], s["bs"]))
+        run = lambda: orc.paged_decode_oracle(qd, kp, vp, table, lens)  # noqa: E731
+        sample = (f"oracle port (ch07 page gather + ch02 cached attention, fp32) on {s['B']} of C3's 64 sequences")
+    run()                                    # warm-up pass (thread pool, allocator, page faults)
+    times = []
+    for _ in range(max(1, passes)):
         t0 = time.perf_counter()
-        orc.flash_attention_oracle(q, k, v, causal=True, skip_masked_blocks=True)
-        best = min(best, time.perf_counter() - t0)
-    flops = 4.0 * s["B"] * s["Hq"] * s["N"] * s["N"] * s["D"] / 2
-    return flops / best / 1e12, best, torch.get_num_threads()
+        run()
+        times.append(time.perf_counter() - t0)
+    ts = sorted(times)
+    print(json.dumps({"kind": kind, "times_s": times, "median_s": ts[len(ts) // 2], "best_s": ts[0], "work": work,
+                      "policy": pol, "torch_threads": torch.get_num_threads(), "sample": sample}))
 
 
-def cpu_decode_sample():
-    import torch
+def run_cpu_child(kind: str, passes: int) -> dict:
+    """Run `cpu_child_main` in a fresh interpreter with a clean threading environment (torchrun exports
+    OMP_NUM_THREADS=1; a CUDA context, pinned buffers or an NVML sampler thread in the parent must not matter)."""
+    env = {k: v for k, v in os.environ.items()
+           if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "CUDA_VISIBLE_DEVICES")}
+    env["CUDA_VISIBLE_DEVICES"] = ""         # the CPU arm never touches a GPU
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-child", kind, "--cpu-passes", str(passes)],
+                       env=env, capture_output=True, text=True, timeout=1200)
+    if r.returncode != 0:
+        raise RuntimeError(f"CPU baseline child failed: {r.stderr[-2000:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1])
 
-    from oracle import attention_oracle as orc
-    s = CPU_DECODE_SAMPLE
-    q, kp, vp, table, lens = orc.seeded_paged(0xC0FFEE + 3, s["B"], s["Hq"], s["Hkv"], s["D"], s["bs"],
-                                              [s["L"]] * s["B"])
-    t0 = time.perf_counter()
-    orc.paged_decode_oracle(q, kp, vp, table, lens)
-    dt = time.perf_counter() - t0
-    nbytes = decode_bytes(s["B"], s["Hq"], s["Hkv"], s["L"], s["D"], s["bs"])
-    return nbytes / dt / 1e9, dt, torch.get_num_threads()
 
-
-def decode_bytes(B, Hq, Hkv, L, D, bs, elt=2):
-    """Algorithmic bytes of one decode step (SURVEY.md 8(d)): K and V once, q and o, the block table."""
-    return 2 * B * L * Hkv * D * elt + 2 * B * Hq * D * elt + 4 * B * ((L + bs - 1) // bs)
+def cpu_baseline_entry(res: dict, unit: str, scale: float) -> dict:
+    """`cpu_baseline` object from a child result: value = work / MEDIAN pass time (best reported beside it)."""
+    n = len(res["times_s"])
+    return {"value": res["work"] / res["median_s"] / scale, "best": res["work"] / res["best_s"] / scale, "unit": unit,
+            "cores": res["torch_threads"], "kind": "port",
+            "sample": f"{res['sample']}: 1 warm-up + {n} timed passes in a fresh process, median {res['median_s']:.2f} s "
+                      f"(best {res['best_s']:.2f} s); threads = min(affinity {res['policy']['affinity']}, cgroup quota "
+                      f"{res['policy']['cgroup_quota']}, physical cores {res['policy']['physical_cores']}); os.cpu_count() = "
+                      f"{res['policy']['os_cpu_count']}",
+            "pass_times_s": res["times_s"]}
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the reference's CPU path (oracle port), rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port) on the whole C2 step, rank 0 only.  The host does not
+    scale with --gpus: at N > 1 the line is the same single-host number, printed as context."""
     if rank != 0:
         return
-    import torch
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm is meant to use every host core
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    s = CPU_SAMPLE
-    for _ in range(min(args.warmup, 1)):
-        cpu_prefill_sample()
-    times = []
-    for _ in range(max(1, min(args.steps, 3))):
-        _, dt, threads = cpu_prefill_sample()
-        times.append(dt)
-    dt = sum(times) / len(times)
-    flops = 4.0 * s["B"] * s["Hq"] * s["N"] * s["N"] * s["D"] / 2
-    val = flops / dt / 1e12
-    sample = (f"oracle port of ch06.flash_attention_forward (+ch01 causal mask, GQA map), fp32, on B{s['B']} x "
-              f"{s['Hq']}q/{s['Hkv']}kv heads x N{s['N']} x D{s['D']} of C2 (1/4 of one GPU's step), "
-              f"{len(times)} timed passes")
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded N(0,1))",
-            "config": config_dict(args.gpus),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "host": {"cpu_count": os.cpu_count(), "torch_threads": torch.get_num_threads()}}
+    passes = max(1, min(args.steps, 3))
+    res = run_cpu_child("prefill", passes)
+    cb = cpu_baseline_entry(res, UNIT, 1e12)
+    cfg = c2_config(1)
+    cfg["note"] = ("host CPU arm: one full C2 step per pass on this box's host cores; it does not scale with --gpus "
+                   "(at N > 1 this is the same single-host figure, for context only)")
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": passes, "warmup": 1, "ms_per_step": res["median_s"] * 1e3, "higher_is_better": True,
+            "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded N(0,1))", "config": cfg, "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "host": res["policy"]}
     emit(line)
 
 
-def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
-    """BASELINE configs 4 and 5: fixed total work, KV heads sharded over the ranks (8/W KV heads + their 32/W q
-    heads per GPU), no data-path collective; the optional NCCL all-gather of O is timed separately.
-    Reported per config: whole-job rate = total algorithmic work / max-over-ranks kernel time."""
-    import torch
-    Hq, Hkv, D = 32, 8, 128
-    if Hkv % world != 0:
-        return {"skipped": f"{Hkv} KV heads do not divide over {world} ranks"}
-    shard = pli.make_shard(rank, world, Hq, Hkv, 1)
-    hq_l, hkv_l = shard.q_end - shard.q_start, shard.kv_end - shard.kv_start
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    out = {}
+# ------------------------------------------------------------------------------------------------
+# helpers shared by the GPU legs
+# ------------------------------------------------------------------------------------------------
+class Timer:
+    def __init__(self, torch, dist, dev, world):
+        self.torch, self.dist, self.dev, self.world = torch, dist, dev, world
+        self.e0, self.e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(fn, warm, reps):
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok: bool) -> bool:
+        return self.max_over_ranks(0.0 if ok else 1.0) == 0.0
+
+    def timed(self, fn, warm, reps):
+        """ms per call: `warm` untimed calls, then `reps` calls between CUDA events on the current stream, bracketed
+        by barrier + synchronize; max over ranks."""
         for _ in range(warm):
             fn()
-        barrier()
-        e0.record()
+        self.barrier()
+        self.e0.record()
         for _ in range(reps):
             fn()
-        e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1) / reps)
+        self.e1.record()
+        self.barrier()
+        return self.max_over_ranks(self.e0.elapsed_time(self.e1) / reps)
 
-    # C4: long-context causal prefill, N = 65536, B = 1
-    N = 65536
-    g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 4 + rank)
-    q = torch.randn(1, hq_l, N, D, device=dev, generator=g).bfloat16()
-    k = torch.randn(1, hkv_l, N, D, device=dev, generator=g).bfloat16()
-    v = torch.randn(1, hkv_l, N, D, device=dev, generator=g).bfloat16()
-    ms = timed(lambda: pli.flash_attention_forward(q, k, v, causal=True), 2, 5)
-    flops = pli.prefill_algorithmic_flops(1, Hq, N, N, D, True)
-    entry = {"workload": "C4: causal GQA prefill N65536 B1 32q/8kv D128 bf16, KV heads sharded", "ms": ms,
-             "tflops_total": flops / (ms * 1e-3) / 1e12, "tflops_per_gpu": flops / world / (ms * 1e-3) / 1e12}
-    if world > 1:
-        o = pli.flash_attention_forward(q, k, v, causal=True)
-        entry["gather_ms"] = timed(lambda: pli.gather_heads(o, shard), 1, 3)
-        entry["gather_bytes_total"] = Hq * N * D * 2
-        # prefill followed by the NCCL all-gather of O, against the kernel whose epilogue TMA-stores every O tile to
-        # all ranks over NVLink (+ flag wait): both leave the full (1, 32, N, D) output on every rank
-        entry["prefill_plus_nccl_gather_ms"] = timed(
-            lambda: pli.gather_heads(pli.flash_attention_forward(q, k, v, causal=True), shard), 1, 3)
-        po4 = pli.PeerOutput(1, Hq, D, torch.bfloat16, shard, device=dev, seq_len=N)
-        entry["prefill_fused_gather_ms"] = timed(
-            lambda: pli.flash_attention_forward(q, k, v, causal=True, peer_out=po4), 2, 5)
-        del po4
-    out["c4_prefill_65536"] = entry
-    del q, k, v
 
-    # C5: decode B256, paged, ctx sweep
-    B, bs = 256, 16
+def sampled_prefill_error(torch, o, q, k, v, rows, heads, group):
+    """CHECKER (oracle/): max |o - oracle| over sampled (q head, row) pairs of a causal prefill, each evaluated as a
+    one-token decode over keys [0, row] with the oracle's ch02 maths.  o/q (1, Hq, N, D), k/v (1, Hkv, N, D) local."""
+    from oracle import attention_oracle as orc
+    worst = 0.0
+    for h in heads:
+        hk = h // group
+        kc = k[0, hk].float().cpu().unsqueeze(0).unsqueeze(2)
+        vc = v[0, hk].float().cpu().unsqueeze(0).unsqueeze(2)
+        for i in rows:
+            ro, _ = orc.cached_attention_oracle(q[:, h:h + 1, i:i + 1].float().cpu(), kc, vc, i + 1)
+            worst = max(worst, (o[:, h:h + 1, i:i + 1].float().cpu() - ro).abs().max().item())
+    return worst
+
+
+def h2d_probe(torch, T, dev, rank, world):
+    """Host <-> device copy rates of one rank's pinned buffer: alone (ranks take turns) and with every rank copying at
+    once — what bounds the end-to-end numbers.  GB/s per GPU."""
+    n = 256 << 20
+    host = torch.empty(n, dtype=torch.uint8).pin_memory()
+    devb = torch.empty(n, dtype=torch.uint8, device=dev)
+
+    def rate(fn, reps=4):
+        fn()
+        torch.cuda.synchronize()
+        T.e0.record()
+        for _ in range(reps):
+            fn()
+        T.e1.record()
+        torch.cuda.synchronize()
+        return n * reps / (T.e0.elapsed_time(T.e1) * 1e-3) / 1e9
+
+    h2d = lambda: devb.copy_(host, non_blocking=True)  # noqa: E731
+    d2h = lambda: host.copy_(devb, non_blocking=True)  # noqa: E731
+    alone_h2d = alone_d2h = 0.0
+    for r in range(world):                        # one rank at a time
+        T.barrier()
+        if r == rank:
+            alone_h2d, alone_d2h = rate(h2d), rate(d2h)
+    T.barrier()
+    conc_h2d = rate(h2d)
+    T.barrier()
+    conc_d2h = rate(d2h)
+    T.barrier()
+    out = {"h2d_gbs_per_gpu_alone": alone_h2d, "d2h_gbs_per_gpu_alone": alone_d2h,
+           "h2d_gbs_per_gpu_all_ranks_at_once": conc_h2d, "d2h_gbs_per_gpu_all_ranks_at_once": conc_d2h}
+    if world > 1:                                  # slowest rank's view
+        for kname in list(out):
+            out[kname] = -T.max_over_ranks(-out[kname])
+        out["aggregate_h2d_gbs_all_ranks_at_once"] = out["h2d_gbs_per_gpu_all_ranks_at_once"] * world
+        out["note"] = ("min over ranks; pinned buffers allocated by the rank's own process after torch.cuda.set_device "
+                       "(first-touch NUMA placement); this pool's boxes expose ONE NUMA node / CPU affinity set for all "
+                       "eight GPUs, so there is no closer node to bind to: when per-GPU rates fall with the rank count the "
+                       "ceiling is the host side (root complex / memory), not NVLink or the kernels")
+    del host, devb
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# N = 1 legs
+# ------------------------------------------------------------------------------------------------
+def prefill_shape_rows(torch, pli, T, dev, peaks):
+    """Off-headline prefill shapes, device-timed like the headline (inputs resident, >= 3 warm-ups), each with its own
+    roofline fraction against the measured burst peak."""
     rows = []
-    shard5 = pli.make_shard(rank, world, Hq, Hkv, B)
-    peer_out = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard5, device=dev) if world > 1 else None
+
+    def add(name, B, Hq, Hkv, N, D, causal, dtype, reps, paged=False):
+        g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 7)
+        q = torch.randn(B, Hq, N, D, device=dev, generator=g).to(dtype)
+        flops = pli.prefill_algorithmic_flops(B, Hq, N, N, D, causal)
+        if paged:
+            bs = 16
+            P = B * N // bs
+            kp = torch.empty(P, 1, bs, Hkv, D, device=dev, dtype=dtype).normal_(generator=g)
+            vp = torch.empty(P, 1, bs, Hkv, D, device=dev, dtype=dtype).normal_(generator=g)
+            table = torch.randperm(P, generator=torch.Generator().manual_seed(3)).to(torch.int32).view(B, N // bs).to(dev)
+            lens = torch.full((B,), N, dtype=torch.int32, device=dev)
+            fn = lambda: pli.flash_attention_paged(q, kp, vp, table, lens, max_seq_len=N)  # noqa: E731
+        else:
+            k = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dtype)
+            v = torch.randn(B, Hkv, N, D, device=dev, generator=g).to(dtype)
+            fn = lambda: pli.flash_attention_forward(q, k, v, causal=causal)  # noqa: E731
+        ms = T.timed(fn, 3, reps)
+        tf = flops / (ms * 1e-3) / 1e12
+        rows.append({"workload": name, "ms": ms, "tflops": tf,
+                     "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_tflops"], "unit": UNIT,
+                                  "frac": tf / peaks["bf16_tflops"], "frac_of_datasheet_2250": tf / 2250.0}})
+
+    bf, hf = torch.bfloat16, torch.float16
+    add("C2 shape, NON-causal (B4 32q/8kv N8192 D128 bf16)", 4, 32, 8, 8192, 128, False, bf, 10)
+    add("causal N2048 (B16 32q/8kv D128 bf16)", 16, 32, 8, 2048, 128, True, bf, 20)
+    add("causal N512 (B64 32q/8kv D128 bf16)", 64, 32, 8, 512, 128, True, bf, 20)
+    add("C2 in fp16", 4, 32, 8, 8192, 128, True, hf, 10)
+    add("causal D64 (B4 32q/8kv N8192 D64 bf16)", 4, 32, 8, 8192, 64, True, bf, 10)
+    add("C2 read in place from 16-token pages (paged prefill)", 4, 32, 8, 8192, 128, True, bf, 10, paged=True)
+    return rows
+
+
+def decode_c3(torch, pli, T, dev, rank, peaks, args):
+    d = C3
+    pages = d["B"] * d["L"] // d["bs"]
+    gd = torch.Generator(device=dev).manual_seed(0xC0FFEE + 3 + rank)
+    pools = [(torch.empty(pages, 1, d["bs"], d["Hkv"], d["D"], device=dev, dtype=torch.bfloat16).normal_(generator=gd),
+              torch.empty(pages, 1, d["bs"], d["Hkv"], d["D"], device=dev, dtype=torch.bfloat16).normal_(generator=gd))
+             for _ in range(3)]
+    table = torch.randperm(pages, generator=torch.Generator().manual_seed(5)).to(torch.int32).view(d["B"], d["L"] // d["bs"]).to(dev)
+    lens = torch.full((d["B"],), d["L"], dtype=torch.int32, device=dev)
+    qd = torch.randn(d["B"], d["Hq"], 1, d["D"], device=dev, generator=gd).bfloat16()
+    splits = pli.decode_num_splits(d["B"], d["Hkv"], d["L"])
+    ws = pli.decode_workspace(d["B"], d["Hq"], d["D"], splits, dev)
+    out = torch.empty(d["B"], d["Hq"], d["D"], dtype=torch.bfloat16, device=dev)
+    dsteps = max(args.steps, 30)
+    state = {"i": 0}
+
+    def step():
+        i = state["i"]
+        state["i"] += 1
+        pli.flash_decode(qd, *pools[i % 3], lens, block_tables=table, max_seq_len=d["L"], workspace=ws, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    pli.reset_launch_count()
+    d_ms = T.timed(step, 0, dsteps)
+    d_launches = pli.launch_count()
+    nbytes = decode_bytes(d["B"], d["Hq"], d["Hkv"], d["L"], d["D"], d["bs"])
+    gbs = nbytes / (d_ms * 1e-3) / 1e9
+    del pools
+    return {"metric": "paged_decode_kv_gbs", "value": gbs * T.world, "unit": "GB/s", "us_per_step": d_ms * 1e3,
+            "steps": dsteps, "gpu_launches": int(d_launches), "num_splits": splits,
+            "config": {"workload": "C3: paged decode, batch 64 per GPU, ctx 4096, 32q/8kv, D128, 16-token pages, bf16",
+                       "l2_policy": "three 1 GiB K/V pool pairs rotated (each larger than L2)"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
+                         "frac_of_8tbs": gbs / 8000.0, "traffic": load_traffic("decode_tma_kernel<128,bf16> C3"),
+                         "algorithmic_bytes": nbytes,
+                         "note": "one split-KV launch per step (a single split writes the output directly; the combine pass "
+                                 "runs only when num_splits > 1); algorithmic bytes = K,V once + q,o + table"}}
+
+
+def decode_c5_sweep(torch, pli, T, dev, rank, world):
+    """BASELINE config 5: decode B256, paged, ctx sweep, KV heads sharded (8/W KV heads + their q heads per GPU).  With
+    W > 1 the fused gather (one launch whose stores scatter O to every rank over NVLink + the flag wait) is timed against
+    decode + NCCL all-gather, and CHECKED: fused == NCCL-gathered bit for bit, sampled sequences against the oracle."""
+    Hq, Hkv, D, B, bs = 32, 8, 128, 256, 16
+    if Hkv % world != 0:
+        return {"skipped": f"{Hkv} KV heads do not divide over {world} ranks"}
+    shard = pli.make_shard(rank, world, Hq, Hkv, B)
+    hq_l, hkv_l = shard.q_end - shard.q_start, shard.kv_end - shard.kv_start
+    g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 5 + rank)
+    peer_out = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard, device=dev) if world > 1 else None
+    rows = []
     for L in (1024, 8192, 32768):
         pages = B * L // bs
         kp = torch.empty(pages, 1, bs, hkv_l, D, device=dev, dtype=torch.bfloat16).normal_(generator=g)
@@ -283,58 +477,180 @@ def run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks):
         ws = pli.decode_workspace(B, hq_l, D, splits, dev)
         od = torch.empty(B, hq_l, D, device=dev, dtype=torch.bfloat16)
         fn = lambda: pli.flash_decode(qd, kp, vp, lens, block_tables=table, max_seq_len=L, workspace=ws, out=od)  # noqa: E731
-        ms = timed(fn, 3, 20 if L < 32768 else 8)
-        # the same step as CUDA-graph replays (10 steps per graph): short contexts are launch-gap-bound otherwise
+        ms = T.timed(fn, 3, 20 if L < 32768 else 8)
         reps_g = 10
         side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            fn()
-            torch.cuda.synchronize()
-            with torch.cuda.graph(graph):
-                for _ in range(reps_g):
-                    fn()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        ms_graph = timed(graph.replay, 1, 4 if L < 32768 else 2) / reps_g
-        del graph
+
+        def graphed(step, after=None):
+            g_ = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                step()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g_):
+                    for _ in range(reps_g):
+                        step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+
+            def replay():
+                g_.replay()
+                if after is not None:
+                    after()
+            t = T.timed(replay, 1, 4 if L < 32768 else 2) / reps_g
+            del g_
+            return t * 1e3
+
+        us_graph = graphed(fn)
         nbytes = decode_bytes(B, Hq, Hkv, L, D, bs)
-        row = {"ctx": L, "us": ms * 1e3, "gbs_total": nbytes / (ms * 1e-3) / 1e9, "gbs_per_gpu": nbytes / world / (ms * 1e-3) / 1e9,
-               "graph_us": ms_graph * 1e3, "graph_gbs_per_gpu": nbytes / world / (ms_graph * 1e-3) / 1e9,
-               "kv_bytes_per_gpu": 2 * pages * bs * hkv_l * D * 2, "l2_note": "single pool; >L2 except ctx 1024 at 8 GPUs"}
+        row = {"ctx": L, "us": ms * 1e3, "gbs_total": nbytes / (ms * 1e-3) / 1e9,
+               "gbs_per_gpu": nbytes / world / (ms * 1e-3) / 1e9, "graph_us": us_graph,
+               "graph_gbs_per_gpu": nbytes / world / (us_graph * 1e-6) / 1e9, "kv_bytes_per_gpu": 2 * pages * bs * hkv_l * D * 2,
+               "l2_note": "single pool; larger than L2 except ctx 1024 at 8 GPUs (128 MiB)"}
+        # parity at size on this rank's shard: three sampled sequences against the oracle (CHECKER)
+        from oracle import attention_oracle as orc
+        fn()
+        err = 0.0
+        for b in (0, B // 2 + 1, B - 1):
+            pg = table[b].long()
+            kg = kp[pg, 0].reshape(1, L, hkv_l, D).cpu()
+            vg = vp[pg, 0].reshape(1, L, hkv_l, D).cpu()
+            ro, _ = orc.cached_attention_oracle(qd[b:b + 1].cpu(), kg, vg, L)
+            err = max(err, (od[b:b + 1].float().cpu().unsqueeze(2) - ro).abs().max().item())
+        parity = {"oracle_max_abs_err": T.max_over_ranks(err), "tolerance": 2e-2, "sampled_sequences_per_rank": 3}
         if world > 1:
-            row["gather_us"] = timed(lambda: pli.gather_heads(od, shard), 2, 10) * 1e3
-            # decode followed by the NCCL all-gather of O, against ONE launch whose stores scatter O to every rank
-            # over NVLink peer memory (+ the flag wait): both leave the full (B, 32, D) output on every rank
+            row["gather_us"] = T.timed(lambda: pli.gather_heads(od, shard), 2, 10) * 1e3
             both = lambda: (fn(), pli.gather_heads(od, shard))  # noqa: E731
-            row["decode_plus_nccl_gather_us"] = timed(both, 2, 10) * 1e3
+            row["decode_plus_nccl_gather_us"] = T.timed(both, 2, 10) * 1e3
             fused = lambda: pli.flash_decode(qd, kp, vp, lens, block_tables=table, max_seq_len=L, workspace=ws,  # noqa: E731
                                              peer_out=peer_out)
-            row["decode_fused_gather_us"] = timed(fused, 3, 10) * 1e3
-
-            def graphed(step, after=None):
-                g_ = torch.cuda.CUDAGraph()
-                side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(side):
-                    step()
-                    torch.cuda.synchronize()
-                    with torch.cuda.graph(g_):
-                        for _ in range(reps_g):
-                            step()
-                torch.cuda.current_stream(dev).wait_stream(side)
-
-                def replay():
-                    g_.replay()
-                    if after is not None:
-                        after()
-                t = timed(replay, 1, 4 if L < 32768 else 2) / reps_g
-                del g_
-                return t * 1e3
+            row["decode_fused_gather_us"] = T.timed(fused, 3, 10) * 1e3
             row["graph_decode_plus_nccl_gather_us"] = graphed(both)
             row["graph_decode_fused_gather_us"] = graphed(fused, lambda: peer_out.advance(reps_g))
+            ref = pli.gather_heads(od, shard)
+            eq = True
+            for _ in range(3):
+                eq = eq and torch.equal(fused(), ref)
+            parity["fused_eq_nccl"] = T.all_true(eq)
+        parity["ok"] = parity["oracle_max_abs_err"] <= 2e-2 and parity.get("fused_eq_nccl", True)
+        row["parity"] = parity
         rows.append(row)
         del kp, vp
-    out["c5_decode_b256"] = {"workload": "C5: paged decode B256, 32q/8kv D128, 16-token pages, KV heads sharded", "sweep": rows}
+    return {"workload": "C5: paged decode B256, 32q/8kv D128, 16-token pages, KV heads sharded", "sweep": rows}
+
+
+def c4_leg(torch, pli, T, dev, rank, world, args, peaks):
+    """BASELINE config 4 on `world` GPUs (KV-head groups sharded, fused all-gather when world > 1).  Returns the dict of
+    measurements; at world > 1 this is the headline."""
+    c = C4
+    Hq, Hkv, N, D = c["Hq"], c["Hkv"], c["N"], c["D"]
+    G = Hq // Hkv
+    shard = pli.make_shard(rank, world, Hq, Hkv, 1)
+    kv_l = range(shard.kv_start, shard.kv_end)
+    # one consistent global problem: KV group g (its k, v head and its 4 q heads) is generated from seed(g) on the host
+    host = {"q": torch.empty(1, len(kv_l) * G, N, D, dtype=torch.bfloat16).pin_memory(),
+            "k": torch.empty(1, len(kv_l), N, D, dtype=torch.bfloat16).pin_memory(),
+            "v": torch.empty(1, len(kv_l), N, D, dtype=torch.bfloat16).pin_memory()}
+    for j, gidx in enumerate(kv_l):
+        gg = torch.Generator().manual_seed(0xC0FFEE + 400 + gidx)
+        host["q"][0, j * G:(j + 1) * G] = torch.randn(G, N, D, generator=gg).to(torch.bfloat16)
+        host["k"][0, j] = torch.randn(N, D, generator=gg).to(torch.bfloat16)
+        host["v"][0, j] = torch.randn(N, D, generator=gg).to(torch.bfloat16)
+    q, k, v = (host[n].to(dev, non_blocking=True) for n in ("q", "k", "v"))
+    torch.cuda.synchronize()
+    flops = pli.prefill_algorithmic_flops(1, Hq, N, N, D, True)
+    out = {}
+    plain = lambda: pli.flash_attention_forward(q, k, v, causal=True)  # noqa: E731
+    if world == 1:
+        ms = T.timed(plain, 2, 5)
+        out.update({"workload": "C4: causal GQA prefill N65536 B1 32q/8kv D128 bf16 on one GPU", "ms": ms,
+                    "tflops_total": flops / (ms * 1e-3) / 1e12})
+        o = plain()
+        err = sampled_prefill_error(torch, o, q, k, v, [0, 127, 128, 32768, N - 1], [0, 13, 31], G)
+        out["parity"] = {"oracle_max_abs_err": err, "tolerance": 2e-2, "ok": err <= 2e-2,
+                         "sampled": "rows 0,127,128,32768,65535 of q heads 0,13,31"}
+        return out
+
+    po = pli.PeerOutput(1, Hq, D, torch.bfloat16, shard, device=dev, seq_len=N)
+    fused = lambda: pli.flash_attention_forward(q, k, v, causal=True, peer_out=po)  # noqa: E731
+    for _ in range(args.warmup):
+        fused()
+    pli.reset_launch_count()
+    with ClockSampler(dev.index) as clocks:
+        ms = T.timed(fused, 0, args.steps)
+    out["launches"] = pli.launch_count()
+    out["clocks"] = clocks.summary()
+    out["ms_per_step"] = ms
+    out["value"] = flops / (ms * 1e-3) / 1e12
+    out["kernel_only_ms"] = T.timed(plain, 1, 5)
+    out["kernel_plus_nccl_gather_ms"] = T.timed(lambda: pli.gather_heads(plain(), shard), 1, 3)
+    out["nccl_gather_alone_ms"] = (lambda o_: T.timed(lambda: pli.gather_heads(o_, shard), 1, 3))(plain())
+    # ---- parity of the fused compute + collective kernel, every run (the driver's SCALE run sees these keys) ----
+    ref = pli.gather_heads(plain(), shard)
+    eq = True
+    for _ in range(2):
+        eq = eq and torch.equal(fused(), ref)
+    full = fused()
+    # every rank checks rows of heads it did NOT compute as well: head h of the full tensor against the K/V of group h // G,
+    # which only its owner holds -> each rank checks its own heads in the full tensor it RECEIVED a copy of, plus (bitwise)
+    # that all ranks hold the same full tensor
+    own = list(range(shard.q_start, shard.q_end))
+    heads = sorted({own[0], own[-1]})
+    err = 0.0
+    for h in heads:
+        hk_local = (h - shard.q_start) // G
+        kc = k[0, hk_local].float().cpu().unsqueeze(0).unsqueeze(2)
+        vc = v[0, hk_local].float().cpu().unsqueeze(0).unsqueeze(2)
+        from oracle import attention_oracle as orc
+        for i in (0, 127, 128, 32768, N - 1):
+            ro, _ = orc.cached_attention_oracle(q[:, h - shard.q_start:h - shard.q_start + 1, i:i + 1].float().cpu(), kc, vc, i + 1)
+            err = max(err, (full[:, h:h + 1, i:i + 1].float().cpu() - ro).abs().max().item())
+    csum = full.view(torch.int16).to(torch.int64).sum()
+    lo, hi = csum.clone(), csum.clone()
+    T.dist.all_reduce(lo, op=T.dist.ReduceOp.MIN)
+    T.dist.all_reduce(hi, op=T.dist.ReduceOp.MAX)
+    out["parity"] = {"fused_eq_nccl": T.all_true(eq), "all_ranks_hold_identical_bits": bool(lo.item() == hi.item()),
+                     "oracle_max_abs_err": T.max_over_ranks(err), "tolerance": 2e-2,
+                     "sampled": "rows 0,127,128,32768,65535 of the first and last q head of every rank, in the gathered tensor"}
+    out["parity"]["ok"] = (out["parity"]["fused_eq_nccl"] and out["parity"]["all_ranks_hold_identical_bits"]
+                           and out["parity"]["oracle_max_abs_err"] <= 2e-2)
+    # ---- the same job on ONE GPU of this box (rank 0, the others idle): the strong-scaling reference of this run ----
+    t1 = 0.0
+    if rank == 0:
+        gq = torch.Generator(device=dev).manual_seed(1)
+        qf = torch.randn(1, Hq, N, D, device=dev, generator=gq).bfloat16()
+        kf = torch.randn(1, Hkv, N, D, device=dev, generator=gq).bfloat16()
+        vf = torch.randn(1, Hkv, N, D, device=dev, generator=gq).bfloat16()
+        for _ in range(2):
+            pli.flash_attention_forward(qf, kf, vf, causal=True)
+        torch.cuda.synchronize()
+        T.e0.record()
+        for _ in range(3):
+            pli.flash_attention_forward(qf, kf, vf, causal=True)
+        T.e1.record()
+        torch.cuda.synchronize()
+        t1 = T.e0.elapsed_time(T.e1) / 3
+        del qf, kf, vf
+    t1 = T.max_over_ranks(t1)
+    out["one_gpu_same_job_ms"] = t1
+    out["strong_scaling_efficiency_vs_one_gpu_of_this_box"] = t1 / (world * ms)
+    # ---- end to end: every rank copies its shard of q,k,v from pinned host memory, runs the fused step, and copies ITS
+    #      heads of the gathered output back (the host receives the full tensor exactly once across the ranks) ----
+    host_o = torch.empty(1, shard.q_end - shard.q_start, N, D, dtype=torch.bfloat16).pin_memory()
+
+    def e2e_step():
+        qd = host["q"].to(dev, non_blocking=True)
+        kd = host["k"].to(dev, non_blocking=True)
+        vd = host["v"].to(dev, non_blocking=True)
+        of = pli.flash_attention_forward(qd, kd, vd, causal=True, peer_out=po)
+        host_o.copy_(of[:, shard.q_start:shard.q_end], non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 8))
+    e2e_ms = T.timed(e2e_step, 2, e2e_steps)
+    out["e2e"] = {"value": flops / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                  "h2d_bytes_per_step": 2 * N * D * (Hq + 2 * Hkv), "d2h_bytes_per_step": 2 * N * D * Hq,
+                  "note": "bytes are totals over all ranks; per step every rank: H2D of its q/k/v shard from pinned memory, the "
+                          "fused prefill + gather, D2H of its own heads of the gathered O"}
+    del po
     return out
 
 
@@ -351,7 +667,13 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-sustained", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true")
+    ap.add_argument("--cpu-child", default=None, choices=["prefill", "decode"], help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-passes", type=int, default=3, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_child:
+        cpu_child_main(args.cpu_child, args.cpu_passes)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     protect_stdout()
 
@@ -371,18 +693,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     peaks = load_peaks()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(ms: float) -> float:
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    T = Timer(torch, dist, dev, world)
 
     # ---- C2 shard of this rank: synthetic bf16 q/k/v generated on the host (pinned), copied once ----
     c = C2
@@ -392,29 +703,66 @@ def main():
         t = torch.empty(c["B"], heads, c["N"], c["D"], dtype=torch.bfloat16).pin_memory()
         t.copy_(torch.randn(c["B"], heads, c["N"], c["D"], generator=g).to(torch.bfloat16))
         host[name] = t
-    host_o = torch.empty(c["B"], c["Hq"], c["N"], c["D"], dtype=torch.bfloat16).pin_memory()
     q, k, v = (host[n].to(dev, non_blocking=True) for n in ("q", "k", "v"))
     torch.cuda.synchronize()
     flops_step = pli.prefill_algorithmic_flops(c["B"], c["Hq"], c["N"], c["N"], c["D"], True)
     assert pli.prefill_kernel_kind(q, k, v) == "tcgen05"
+    c2_step = lambda: pli.flash_attention_forward(q, k, v, causal=True)  # noqa: E731
 
-    # ---- device-resident timing: W warm-ups, exactly K steps between events ----
+    # ---- C2 device-resident timing: W warm-ups, exactly K steps between events (the headline at N = 1; `weak_c2` at N > 1,
+    #      where a handful of steps is enough) ----
+    c2_steps = args.steps if world == 1 else min(args.steps, 10)
     for _ in range(args.warmup):
-        o = pli.flash_attention_forward(q, k, v, causal=True)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c2_step()
     pli.reset_launch_count()
     with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            o = pli.flash_attention_forward(q, k, v, causal=True)
-        e1.record()
-        barrier()
+        ms_step = T.timed(c2_step, 0, c2_steps)
     launches = pli.launch_count()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
     value = flops_step * world / (ms_step * 1e-3) / 1e12
 
+    if world > 1:
+        # ================= N > 1: the partitioned workload (C4, strong scaling, fused all-gather) is the headline =================
+        c4 = c4_leg(torch, pli, T, dev, rank, world, args, peaks)
+        probe = h2d_probe(torch, T, dev, rank, world)
+        strong = None
+        if not args.no_strong:
+            strong = {"c5_decode_b256": decode_c5_sweep(torch, pli, T, dev, rank, world)}
+        if rank == 0:
+            flops4 = pli.prefill_algorithmic_flops(1, C4["Hq"], C4["N"], C4["N"], C4["D"], True)
+            per_gpu = c4["value"] / world
+            nv_bytes = 2 * C4["N"] * C4["D"] * (C4["Hq"] // world) * (world - 1)          # this rank's O shard to W-1 peers
+            t_compute = flops4 / world / (peaks["bf16_tflops"] * 1e12) * 1e3
+            t_link = nv_bytes / 770e9 * 1e3
+            e2e = c4.pop("e2e")
+            e2e.update(probe)
+            line = {
+                "metric": METRIC, "value": c4["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": c4["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic (seeded N(0,1), random-init)",
+                "config": c4_config(world), "clocks": c4.pop("clocks"), "e2e": e2e, "gpu_launches": int(c4.pop("launches")),
+                "parity": c4.pop("parity"),
+                "roofline": {"bound": "tensor", "achieved": per_gpu, "peak": peaks["bf16_tflops"], "unit": UNIT,
+                             "frac": per_gpu / peaks["bf16_tflops"],
+                             "peak_source": peaks["source"] + " cuBLAS bf16 burst, per GPU",
+                             "frac_of_datasheet_2250": per_gpu / 2250.0,
+                             "fused_collective": {"target_ms": max(t_compute, t_link), "compute_ms_at_peak": t_compute,
+                                                  "nvlink_ms_at_770GBs": t_link, "nvlink_bytes_per_gpu": nv_bytes,
+                                                  "achieved_over_target": max(t_compute, t_link) / c4["ms_per_step"]},
+                             "traffic": None, "kernel": "prefill_tcgen05_kernel<128,bf16> with peer TMA stores",
+                             "flops_per_launch": flops4 / world},
+                "c4": c4,
+                "weak_c2": {"value": value, "unit": UNIT, "ms_per_step": ms_step, "steps": c2_steps, "scaling": "weak",
+                            "per_gpu": value / world, "clocks": clocks.summary(), "gpu_launches": int(launches),
+                            "config": c2_config(world)},
+            }
+            if strong is not None:
+                line["strong_scaling_configs"] = strong
+            emit(line)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
+    # ================= N = 1 =================
     # ---- sustained: the same step back to back for ~1.5 s (B200 is power-capped at 1 kW under this kernel;
     #      the K-step region above is short enough to run mostly before the cap engages) ----
     sustained = None
@@ -422,24 +770,20 @@ def main():
         n_warm = max(10, int(600.0 / ms_step))
         n_meas = max(10, int(900.0 / ms_step))
         for _ in range(n_warm):
-            o = pli.flash_attention_forward(q, k, v, causal=True)
+            c2_step()
         with ClockSampler(local) as sclocks:
-            e0.record()
-            for _ in range(n_meas):
-                o = pli.flash_attention_forward(q, k, v, causal=True)
-            e1.record()
-            barrier()
-        s_ms = max_over_ranks(e0.elapsed_time(e1) / n_meas)
-        s_val = flops_step * world / (s_ms * 1e-3) / 1e12
+            s_ms = T.timed(c2_step, 0, n_meas)
+        s_val = flops_step / (s_ms * 1e-3) / 1e12
         sustained = {"value": s_val, "unit": UNIT, "ms_per_step": s_ms, "steps": n_meas, "after_warm_steps": n_warm,
                      "clocks": sclocks.summary(),
-                     "frac_of_sustained_peak": (s_val / world / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None}
+                     "frac_of_sustained_peak": (s_val / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None}
 
     # ---- end to end through the public API with host buffers (H2D q,k,v; D2H o) ----
     # Every step copies its q,k,v from pinned host memory, calls flash_attention_forward and copies O back.
-    # `serial`: one stream, step after step.  `value`: the same steps software-pipelined over three streams
+    # `serial`: one stream, step after step.  `pipelined`: the same steps software-pipelined over three streams
     # with two device buffer sets (copy-in of step i+1 and copy-out of step i-1 overlap the kernel of step i),
     # which is how a streaming caller would drive it; PCIe (H2D 403 MB per step) is the bound either way.
+    host_o = torch.empty(c["B"], c["Hq"], c["N"], c["D"], dtype=torch.bfloat16).pin_memory()
     e2e_steps = max(4, min(args.steps, 12))
     h2d = sum(host[n].numel() * 2 for n in ("q", "k", "v"))
     d2h = host_o.numel() * 2
@@ -451,15 +795,7 @@ def main():
         od = pli.flash_attention_forward(qd, kd, vd, causal=True)
         host_o.copy_(od, non_blocking=True)
 
-    for _ in range(2):
-        e2e_serial_step()
-    barrier()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_serial_step()
-    e1.record()
-    barrier()
-    e2e_serial_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+    e2e_serial_ms = T.timed(e2e_serial_step, 2, e2e_steps)
 
     s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     dbuf = [{n: torch.empty_like(t, device=dev) for n, t in host.items()} for _ in range(2)]
@@ -493,119 +829,68 @@ def main():
     e2e_pipelined(2)
     for st in (s_in, s_run, s_out):
         cur.wait_stream(st)
-    barrier()
-    e0.record()
+    T.barrier()
+    T.e0.record()
     for st in (s_in, s_run, s_out):
         st.wait_stream(cur)
     e2e_pipelined(e2e_steps)
     for st in (s_in, s_run, s_out):
         cur.wait_stream(st)
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
-    e2e_val = flops_step * world / (e2e_ms * 1e-3) / 1e12
+    T.e1.record()
+    T.barrier()
+    e2e_ms = T.e0.elapsed_time(T.e1) / e2e_steps
+    e2e_val = flops_step / (e2e_ms * 1e-3) / 1e12
     del dbuf, obuf
+    probe = h2d_probe(torch, T, dev, rank, world)
 
-    # ---- second half of the metric: paged decode C3 (device-timed, three pools > L2 rotated) ----
-    decode = None
-    if not args.no_decode:
-        d = C3
-        pages = d["B"] * d["L"] // d["bs"]
-        gd = torch.Generator(device=dev).manual_seed(0xC0FFEE + 3 + rank)
-        pools = [(torch.randn(pages, 1, d["bs"], d["Hkv"], d["D"], device=dev, generator=gd).bfloat16(),
-                  torch.randn(pages, 1, d["bs"], d["Hkv"], d["D"], device=dev, generator=gd).bfloat16())
-                 for _ in range(3)]
-        table = torch.randperm(pages, generator=torch.Generator().manual_seed(5))[:pages].to(torch.int32)
-        table = table.view(d["B"], d["L"] // d["bs"]).to(dev)
-        lens = torch.full((d["B"],), d["L"], dtype=torch.int32, device=dev)
-        qd = torch.randn(d["B"], d["Hq"], 1, d["D"], device=dev, generator=gd).bfloat16()
-        splits = pli.decode_num_splits(d["B"], d["Hkv"], d["L"])
-        ws = pli.decode_workspace(d["B"], d["Hq"], d["D"], splits, dev)
-        out = torch.empty(d["B"], d["Hq"], d["D"], dtype=torch.bfloat16, device=dev)
-        dsteps = max(args.steps, 30)
-        for i in range(max(args.warmup, 3)):
-            pli.flash_decode(qd, *pools[i % 3], lens, block_tables=table, max_seq_len=d["L"], workspace=ws, out=out)
-        barrier()
-        pli.reset_launch_count()
-        e0.record()
-        for i in range(dsteps):
-            pli.flash_decode(qd, *pools[i % 3], lens, block_tables=table, max_seq_len=d["L"], workspace=ws, out=out)
-        e1.record()
-        barrier()
-        d_launches = pli.launch_count()
-        d_ms = max_over_ranks(e0.elapsed_time(e1) / dsteps)
-        nbytes = decode_bytes(d["B"], d["Hq"], d["Hkv"], d["L"], d["D"], d["bs"])
-        gbs = nbytes / (d_ms * 1e-3) / 1e9
-        decode = {"metric": "paged_decode_kv_gbs", "value": gbs * world, "unit": "GB/s", "us_per_step": d_ms * 1e3,
-                  "steps": dsteps, "gpu_launches": int(d_launches), "num_splits": splits,
-                  "config": {"workload": "C3: paged decode, batch 64 per GPU, ctx 4096, 32q/8kv, D128, 16-token pages, bf16",
-                             "l2_policy": "three 1 GiB K/V pool pairs rotated (each larger than L2)"},
-                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                               "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["source"] + " copy bandwidth",
-                               "frac_of_8tbs": gbs / 8000.0, "traffic": load_traffic("decode_tma_kernel<128,bf16> C3"),
-                               "algorithmic_bytes": nbytes,
-                               "note": "one split-KV launch per step (a single split writes the output directly; the combine pass runs only when num_splits > 1); algorithmic bytes = K,V once + q,o + table"}}
-        del pools
-
-    # ---- strong-scaling configs of BASELINE.json (C4 long-context prefill, C5 decode sweep), KV heads sharded ----
+    decode = None if args.no_decode else decode_c3(torch, pli, T, dev, rank, peaks, args)
+    shapes = None if args.no_shapes else prefill_shape_rows(torch, pli, T, dev, peaks)
     strong = None
     if not args.no_strong:
-        strong = run_strong_configs(pli, dist, dev, rank, world, barrier, max_over_ranks)
+        strong = {"c4_prefill_65536": c4_leg(torch, pli, T, dev, rank, world, args, peaks),
+                  "c5_decode_b256": decode_c5_sweep(torch, pli, T, dev, rank, world)}
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
+    e2e = {"value": max(e2e_val, flops_step / (e2e_serial_ms * 1e-3) / 1e12), "unit": UNIT,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": min(e2e_ms, e2e_serial_ms), "steps": e2e_steps,
+           "driving": "pipelined" if e2e_ms <= e2e_serial_ms else "serial",
+           "pipelined_value": e2e_val, "pipelined_ms_per_step": e2e_ms,
+           "serial_value": flops_step / (e2e_serial_ms * 1e-3) / 1e12, "serial_ms_per_step": e2e_serial_ms,
+           "copy_floor_ms": (h2d / max(probe["h2d_gbs_per_gpu_alone"], 1e-9) / 1e6),
+           "note": "every step: q,k,v copied from pinned host memory, flash_attention_forward, O copied back; "
+                   "pipelined = steps over three streams (double-buffered), serial = one stream; "
+                   "value = the faster of the two on this box; copy_floor_ms = H2D bytes / measured H2D rate: the step "
+                   "cannot be shorter than its own input copy"}
+    e2e.update(probe)
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic (seeded N(0,1), random-init)", "config": config_dict(world),
-        "clocks": clocks.summary(),
-        # both drivings are full end-to-end steps through the public call; the headline is the faster one on this box
-        # (on some hosts the two PCIe directions do not overlap and the single-stream order wins)
-        "e2e": {"value": max(e2e_val, flops_step * world / (e2e_serial_ms * 1e-3) / 1e12), "unit": UNIT,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": min(e2e_ms, e2e_serial_ms), "steps": e2e_steps,
-                "driving": "pipelined" if e2e_ms <= e2e_serial_ms else "serial",
-                "pipelined_value": e2e_val, "pipelined_ms_per_step": e2e_ms,
-                "serial_value": flops_step * world / (e2e_serial_ms * 1e-3) / 1e12, "serial_ms_per_step": e2e_serial_ms,
-                "note": "every step: q,k,v copied from pinned host memory, flash_attention_forward, O copied back; "
-                        "pipelined = steps over three streams (double-buffered), serial = one stream; "
-                        "value = the faster of the two on this box"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": value / world, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": value / world / peaks["bf16_tflops"],
+        "data": "synthetic (seeded N(0,1), random-init)", "config": c2_config(1),
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": value, "peak": peaks["bf16_tflops"], "unit": UNIT,
+                     "frac": value / peaks["bf16_tflops"],
                      "peak_source": peaks["source"] + " cuBLAS bf16 burst (kernel timed alone, back to back)",
-                     "frac_of_sustained": (value / world / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
-                     "frac_of_datasheet_2250": value / world / 2250.0,
+                     "frac_of_sustained": (value / peaks["bf16_tflops_sustained"]) if peaks["bf16_tflops_sustained"] else None,
+                     "frac_of_datasheet_2250": value / 2250.0,
                      "traffic": load_traffic("prefill_tcgen05_kernel<128,bf16> C2"),
                      "algorithmic_bytes": 4 * C2["B"] * C2["N"] * C2["D"] * (C2["Hq"] + C2["Hkv"]),
-                     "kernel": "prefill_tcgen05_kernel<128,bf16>", "flops_per_launch": flops_step},
+                     "kernel": "prefill_tcgen05_kernel<128,bf16,cluster 2,pair MMA>", "flops_per_launch": flops_step},
     }
     if sustained is not None:
         line["sustained"] = sustained
+    if shapes is not None:
+        line["shapes"] = shapes
     if strong is not None:
         line["strong_scaling_configs"] = strong
     if decode is not None:
         line["decode"] = decode
-    if not args.no_cpu_baseline and world == 1:
-        val, dt, threads = cpu_prefill_sample(reps=4)
-        s = CPU_SAMPLE
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"oracle port (ch06 recurrence + ch01 mask/GQA, fp32) on B{s['B']} x {s['Hq']}q/{s['Hkv']}kv "
-                                          f"x N{s['N']} x D{s['D']} of C2 = 1/4 of the step, best of 4 passes ({dt:.1f} s each)"}
+    if not args.no_cpu_baseline:
+        torch.cuda.synchronize()
+        res = run_cpu_child("prefill", 3)
+        line["cpu_baseline"] = cpu_baseline_entry(res, UNIT, 1e12)
         if decode is not None:
-            dval, ddt, _ = cpu_decode_sample()
-            s = CPU_DECODE_SAMPLE
-            line["decode"]["cpu_baseline"] = {"value": dval, "unit": "GB/s", "cores": threads, "kind": "port",
-                                              "sample": f"oracle port (ch07 page gather + ch02 cached attention, fp32) on "
-                                                        f"{s['B']} of the 64 sequences, {ddt:.2f} s"}
+            line["decode"]["cpu_baseline"] = cpu_baseline_entry(run_cpu_child("decode", 3), "GB/s", 1e9)
     emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

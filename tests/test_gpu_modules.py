@@ -126,8 +126,8 @@ def test_cached_generate_on_the_kernels_gives_the_reference_tokens(golden_dir):
     seed, batch, prompt_len, n_new = [int(x) for x in g["meta"]]
     torch.manual_seed(seed)
     model = TinyCachedModel(pli.CachedGQA, vocab, hidden, layers, heads, kv_heads, inter)
-    wsum = np.array([float(p.double().sum()) for p in model.parameters()] +
-                    [float((p.double() ** 2).sum()) for p in model.parameters()])
+    wsum = np.array([float(p.detach().double().sum()) for p in model.parameters()] +
+                    [float((p.detach().double() ** 2).sum()) for p in model.parameters()])
     assert np.allclose(wsum, g["wsum"], rtol=0, atol=1e-9), "seeded weights differ from the reference model's"
     model = model.cuda()
     torch.backends.cuda.matmul.allow_tf32 = False
