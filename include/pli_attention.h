@@ -204,6 +204,24 @@ int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_sto
                            const pli_peer_scatter* ps, void* stream);
 int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream);
 
+/* Copy the output buffer written by the step that has just completed on this stream (its parity is read from the device
+ * step counter) into a FIXED destination of `nbytes` bytes (elements of `elem_size` bytes).  Needed under CUDA-graph
+ * capture: the buffer a replay writes alternates with the step parity, so a consumer captured in the same graph (the output
+ * projection, the next layer) must read from an address that does not.  Launch it after pli_peer_publish_wait. */
+int pli_peer_select_copy(const pli_peer_scatter* ps, void* dst, int64_t nbytes, int elem_size, void* stream);
+
+/* How long pli_peer_publish_wait waits for a peer rank's slice before it gives up (milliseconds of wall time; default
+ * 60 000; 0 = forever).  Giving up does NOT trap: the kernel records the event (below) and the stream continues. */
+int pli_set_peer_timeout_ms(int64_t ms);
+
+/* Host-visible fault record (eight words in host-mapped pinned memory, readable even after a kernel trapped):
+ *   out[0] code: 0 none, 1 an intra-kernel mbarrier wait exceeded its wall-time bound (protocol bug; that kernel trapped),
+ *                2 a peer rank's slice did not arrive within the peer timeout (no trap; the step's output is incomplete);
+ *   out[1] code 1: block << 32 | thread;  code 2: waiting rank << 32 | missing rank;
+ *   out[2] code 1: barrier shared-memory address | parity << 32;  code 2: step number;   out[3] %globaltimer (ns).
+ * clear != 0 resets the record after reading it. */
+int pli_device_status(uint64_t out[8], int clear);
+
 /* Prefill with the same fused all-gather: the epilogue's TMA store of every finished O tile goes to all ranks'
  * full outputs (B_total, Hq_total, Nq, D), so the transfer overlaps the MMAs of the following tiles; follow it with
  * pli_peer_publish_wait.  q/k/v/lse and B, Hq, Hkv describe the LOCAL shard as for pli_prefill_fwd; o_strides

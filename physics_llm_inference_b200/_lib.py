@@ -63,6 +63,9 @@ _SIGNATURES = {
                                           _I64P, _I64P, _I64P, _I64P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.POINTER(PeerScatter), _VP]),
     "pli_peer_publish_wait": (C.c_int, [C.POINTER(PeerScatter), _VP]),
+    "pli_peer_select_copy": (C.c_int, [C.POINTER(PeerScatter), _VP, C.c_int64, C.c_int, _VP]),
+    "pli_set_peer_timeout_ms": (C.c_int, [C.c_int64]),
+    "pli_device_status": (C.c_int, [C.POINTER(C.c_uint64), C.c_int]),
     "pli_kv_append": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, _I64P, _I64P, C.c_int, _VP]),
     "pli_paged_gather": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -115,6 +118,35 @@ def check(rc: int) -> None:
         if rc == -1:
             raise ValueError(f"pli: {msg}")
         raise PliError(f"pli error {rc}: {msg}")
+
+
+FAULT_NAMES = {0: "none", 1: "mbarrier wait timed out inside a kernel (protocol bug; the kernel trapped)",
+               2: "a peer rank's output slice did not arrive within the peer timeout"}
+
+
+def device_status(clear: bool = False) -> dict:
+    """The library's host-visible fault record (include/pli_attention.h: pli_device_status)."""
+    buf = (C.c_uint64 * 8)()
+    check(load().pli_device_status(buf, int(clear)))
+    code = int(buf[0])
+    rec = {"code": code, "what": FAULT_NAMES.get(code, "unknown"), "timer_ns": int(buf[3])}
+    if code == 1:
+        rec.update(block=int(buf[1]) >> 32, thread=int(buf[1]) & 0xFFFFFFFF, barrier_smem_addr=int(buf[2]) & 0xFFFFFFFF,
+                   parity=int(buf[2]) >> 32)
+    elif code == 2:
+        rec.update(waiting_rank=int(buf[1]) >> 32, missing_rank=int(buf[1]) & 0xFFFFFFFF, step=int(buf[2]))
+    return rec
+
+
+def raise_on_device_fault() -> None:
+    rec = device_status()
+    if rec["code"] != 0:
+        device_status(clear=True)
+        raise PliError(f"device fault recorded: {rec}")
+
+
+def set_peer_timeout_ms(ms: int) -> None:
+    check(load().pli_set_peer_timeout_ms(int(ms)))
 
 
 def i64(*vals) -> C.Array:

@@ -43,6 +43,15 @@ inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
                                     cudaGetErrorString(_e), __FILE__, __LINE__);                \
     } while (0)
 
+// Device-fault record: eight 64-bit words in host-mapped pinned memory (allocated once per process, pli_capi.cu), so the
+// host can read WHY a kernel gave up even after a trap has killed the context: [0] code (PLI_FAULT_*), [1] block << 32 |
+// thread, [2] detail (barrier shared-memory address | parity << 32, or peer rank << 32 | step), [3] %globaltimer.
+unsigned long long* status_words();
+uint64_t peer_timeout_ns();
+#define PLI_FAULT_NONE 0
+#define PLI_FAULT_MBARRIER_TIMEOUT 1   /* an intra-kernel mbarrier wait exceeded PLI_MBAR_TIMEOUT_NS: protocol bug; the kernel traps */
+#define PLI_FAULT_PEER_TIMEOUT 2       /* a peer rank's slice did not arrive within the peer timeout: reported, NOT trapped */
+
 // launchers implemented in the per-kernel translation units
 int launch_prefill_simt(const void* q, const void* k, const void* v, void* o, float* lse, int B, int Hq,
                         int Hkv, int Nq, int Nk, int D, const int64_t* qs, const int64_t* ks,
@@ -109,21 +118,45 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch fails with an error) instead of hanging the GPU.
+// Bounded wait: a protocol bug ends the launch with an error instead of hanging the GPU.  The bound is WALL time spent in
+// one wait (%globaltimer, looked at every 2^16 failed probes, i.e. every few milliseconds), generous enough for a
+// debugger or a time-sliced GPU (10 s by default; -DPLI_MBAR_TIMEOUT_NS=0 waits forever), and before trapping the
+// thread writes who waited on what into the host-visible fault record (status_words()).
 #ifndef PLI_MBAR_TIMEOUT_NS
-#define PLI_MBAR_TIMEOUT_NS 4000000000ull
+#define PLI_MBAR_TIMEOUT_NS 10000000000ull
 #endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
     return t;
 }
-// A failed try_wait returns after a short hardware sleep (~50 cycles measured), so 2^26 spins is a
-// watchdog of a couple of seconds without carrying timer code in every wait site.
+// One copy per translation unit (no relocatable device code): bound to status_words() by bind_status_symbol() before
+// the unit's first launch on a device.
+static __constant__ unsigned long long* c_pli_status = nullptr;
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+    unsigned long long* st = c_pli_status;
+    if (st != nullptr) {
+        st[1] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;
+        st[2] = (unsigned long long)bar_addr | ((unsigned long long)parity << 32);
+        st[3] = global_timer_ns();
+        __threadfence_system();
+        st[0] = PLI_FAULT_MBARRIER_TIMEOUT;
+        __threadfence_system();
+    }
+    __trap();
+}
+// slow path of a wait, entered every 2^16 failed probes: t0 = first time seen (0 = not yet)
+__device__ __forceinline__ void mbar_watchdog(uint64_t& t0, uint64_t* bar, uint32_t parity) {
+    if (PLI_MBAR_TIMEOUT_NS == 0) return;
+    const uint64_t now = global_timer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > PLI_MBAR_TIMEOUT_NS) mbar_timeout(smem_u32(bar), parity);
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins == (1u << 26)) __trap();
+        if ((++spins & 0xFFFFu) == 0) mbar_watchdog(t0, bar, parity);
     }
 }
 
@@ -132,6 +165,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // matters on a power-capped part.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     for (;;) {
         uint32_t ok;
         asm volatile(
@@ -142,8 +176,19 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
             : "memory");
         if (ok) return;
-        if (++spins == (1u << 22)) __trap();
+        if ((++spins & 0xFFFu) == 0) mbar_watchdog(t0, bar, parity);     // a probe parks the warp for up to ~1 us
     }
+}
+
+// host side of the fault record: bind this translation unit's c_pli_status on the current device (once per device)
+inline cudaError_t bind_status_symbol() {
+    static thread_local uint64_t bound = 0;
+    const int dev = current_device();
+    if (dev >= 0 && dev < 64 && ((bound >> dev) & 1)) return cudaSuccess;
+    unsigned long long* ptr = status_words();
+    cudaError_t e = cudaMemcpyToSymbol(c_pli_status, &ptr, sizeof(ptr));
+    if (e == cudaSuccess && dev >= 0 && dev < 64) bound |= 1ull << dev;
+    return e;
 }
 
 // ---- cluster-scope mbarrier operations (CTA-pair MMAs: the leader CTA's barriers gate the MMAs of both CTAs) ----

@@ -169,6 +169,8 @@ struct PeerFlags {
     uint32_t* flags[PLI_MAX_PEERS];
     int n, rank;
     uint32_t* epoch;
+    unsigned long long timeout_ns;    // 0: wait forever
+    unsigned long long* status;       // host-visible fault record (common.cuh), or NULL
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
@@ -489,8 +491,11 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __rest
 
 // Runs after the scattering kernel on the same stream (whose peer stores are complete at the kernel boundary).
 // Thread r tells rank r that this rank's slice of `epoch` has landed (release, system scope), then spins (acquire)
-// until rank r's slice has landed here.  Publishing never waits on anybody, so this cannot deadlock; a lost peer
-// traps after ~4 s instead of hanging.
+// until rank r's slice has landed here.  Publishing never waits on anybody, so this cannot deadlock.  A peer that is
+// merely late (lazy module load, host GC, a checkpoint, a debugger) is waited for: the bound is wall time
+// (pli_set_peer_timeout_ms, 60 s by default, 0 = forever), and when it expires the kernel does NOT trap — it records
+// (this rank, the missing rank, the step) in the host-visible fault record, which pli_device_status / PeerOutput.advance
+// turn into an error on the host, and lets the stream continue (the step's output is then incomplete).
 __global__ void peer_publish_wait_kernel(const PeerFlags pf) {
     const int r = threadIdx.x;
     const uint32_t e = *pf.epoch + 1u;
@@ -499,13 +504,39 @@ __global__ void peer_publish_wait_kernel(const PeerFlags pf) {
         __threadfence_system();
         st_release_sys(pf.flags[r] + pf.rank, e);
         const uint32_t* mine = pf.flags[pf.rank] + r;
-        for (long long spin = 0; (int32_t)(ld_acquire_sys(mine) - e) < 0; ++spin) {
+        uint64_t t0 = 0;
+        for (uint32_t spin = 1; (int32_t)(ld_acquire_sys(mine) - e) < 0; ++spin) {
             __nanosleep(32);
-            if (spin > (1ll << 26)) __trap();
+            if ((spin & 0x3FFu) == 0 && pf.timeout_ns != 0) {
+                const uint64_t now = global_timer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > pf.timeout_ns) {
+                    if (pf.status != nullptr) {
+                        pf.status[1] = ((unsigned long long)pf.rank << 32) | (unsigned)r;       // waiting rank | missing rank
+                        pf.status[2] = e;
+                        pf.status[3] = now;
+                        __threadfence_system();
+                        pf.status[0] = PLI_FAULT_PEER_TIMEOUT;
+                        __threadfence_system();
+                    }
+                    break;
+                }
+            }
         }
     }
     __syncwarp();
     if (r == 0) *pf.epoch = e;        // the step is complete on this rank
+}
+
+// Copy the output buffer the step that has just completed wrote (parity read from the device step counter) into a
+// FIXED destination: under CUDA-graph capture the buffer a replay writes alternates, so a consumer captured in the same
+// graph must read from an address that does not (pli_peer_select_copy).
+__global__ void __launch_bounds__(256) peer_select_copy_kernel(const uint4* __restrict__ buf0, int64_t buffer_stride_vec,
+                                                               const uint32_t* __restrict__ epoch, uint4* __restrict__ dst,
+                                                               int64_t n_vec) {
+    const uint4* src = buf0 + (int64_t)(*epoch & 1u) * buffer_stride_vec;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -593,6 +624,7 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
     size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 1024;
     if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, (int)smem));
+    PLI_CUDA_CHECK(bind_status_symbol());
     kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();
@@ -849,7 +881,28 @@ extern "C" int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream) {
     pf.n = ps->n_peers;
     pf.rank = ps->rank;
     pf.epoch = ps->epoch;
+    pf.timeout_ns = peer_timeout_ns();
+    pf.status = status_words();
     peer_publish_wait_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(pf);
+    PLI_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return PLI_OK;
+}
+
+extern "C" int pli_peer_select_copy(const pli_peer_scatter* ps, void* dst, int64_t nbytes, int elem_size, void* stream) {
+    if (!ps || !dst) return set_error(PLI_ERR_INVALID, "null argument");
+    if (ps->rank < 0 || ps->rank >= ps->n_peers || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "bad rank");
+    if (!ps->epoch || !ps->peer_o[ps->rank]) return set_error(PLI_ERR_INVALID, "null epoch word / output pointer");
+    if (nbytes <= 0 || nbytes % 16 || elem_size <= 0 || (ps->buffer_stride * elem_size) % 16 ||
+        ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(ps->peer_o[ps->rank])) & 15))
+        return set_error(PLI_ERR_INVALID, "peer_select_copy needs 16-byte aligned buffers and sizes");
+    const int64_t n_vec = nbytes / 16;
+    int64_t blocks = (n_vec + 255) / 256;
+    const int64_t cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 8;
+    if (blocks > cap) blocks = cap;
+    peer_select_copy_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(ps->peer_o[ps->rank]), ps->buffer_stride * elem_size / 16, ps->epoch,
+        static_cast<uint4*>(dst), n_vec);
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return PLI_OK;

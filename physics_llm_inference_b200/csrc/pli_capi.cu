@@ -32,6 +32,22 @@ EncodeTiledFn get_encode_tiled() {
     return fn;
 }
 
+// Fault record in host-mapped pinned memory (see common.cuh): readable by the host even after a kernel trapped.
+unsigned long long* status_words() {
+    static unsigned long long* words = []() -> unsigned long long* {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, 8 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        memset(p, 0, 8 * sizeof(unsigned long long));
+        return static_cast<unsigned long long*>(p);
+    }();
+    return words;
+}
+static uint64_t g_peer_timeout_ns = 60ull * 1000 * 1000 * 1000;      // 0 = wait forever
+uint64_t peer_timeout_ns() { return g_peer_timeout_ns; }
+
 static thread_local int g_device = -1;
 int current_device() {
     if (g_device < 0) {
@@ -110,6 +126,18 @@ extern "C" int pli_set_device(int device) {
     PLI_CUDA_CHECK(cudaSetDevice(device));
     g_device = device;
     if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "CUDA device %d is not sm_100 (B200)", device);
+    return PLI_OK;
+}
+extern "C" int pli_device_status(uint64_t out[8], int clear) {
+    unsigned long long* w = status_words();
+    if (!out) return set_error(PLI_ERR_INVALID, "null output");
+    for (int i = 0; i < 8; ++i) out[i] = w ? w[i] : 0;
+    if (w && clear) memset(w, 0, 8 * sizeof(unsigned long long));
+    return w ? PLI_OK : set_error(PLI_ERR_CUDA, "the host-mapped fault record could not be allocated");
+}
+extern "C" int pli_set_peer_timeout_ms(int64_t ms) {
+    if (ms < 0) return set_error(PLI_ERR_INVALID, "negative timeout");
+    g_peer_timeout_ns = (uint64_t)ms * 1000000ull;
     return PLI_OK;
 }
 extern "C" uint64_t pli_launch_count(void) { return g_launches; }

@@ -1577,6 +1577,7 @@ int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv
     auto kern = prefill_tcgen05_kernel<kD, kBf16, kCluster, kPaged, kPairMma>;
     const int smem = SmemLayout<kD>::kTotal + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
+    PLI_CUDA_CHECK(bind_status_symbol());
     int grid = sm_count();
     if (grid <= 0) grid = 148;
     if (max_ctas_env() > 0 && grid > max_ctas_env()) grid = max_ctas_env();
@@ -1606,6 +1607,7 @@ int launch_wide(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap&
     auto kern = prefill_wide_kernel<kBf16, kGroups>;
     const int smem = WideLayout::kTotal + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, smem));
+    PLI_CUDA_CHECK(bind_status_symbol());
     int grid = sm_count();
     if (grid <= 0) grid = 148;
     if (max_ctas_env() > 0 && grid > max_ctas_env()) grid = max_ctas_env();
