@@ -464,7 +464,7 @@ def decode_c5_sweep(torch, pli, T, dev, rank, world):
     shard = pli.make_shard(rank, world, Hq, Hkv, B)
     hq_l, hkv_l = shard.q_end - shard.q_start, shard.kv_end - shard.kv_start
     g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 5 + rank)
-    peer_out = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard, device=dev) if world > 1 else None
+    peer_out = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard, device=dev, graph_safe=True) if world > 1 else None
     rows = []
     for L in (1024, 8192, 32768):
         pages = B * L // bs

@@ -455,29 +455,48 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
 // ------------------------------------------------------------------------------------------------
 // combine: merge S partials per (b, q head)
 // ------------------------------------------------------------------------------------------------
+// One CTA per (batch row, q head).  The S partial LSEs are reduced across the lanes of a warp (one or two per lane,
+// S <= 64) instead of three serial passes over them, the weights go through shared memory, and the weighted sum over the
+// partial outputs keeps eight independent, coalesced loads in flight per thread: with few sequences and many splits
+// (B1 x L32768: 37 splits) the old serial loops cost more than the split-KV kernel they followed.
 template <typename T>
 __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __restrict__ o_part,
                                                              const float* __restrict__ lse_part, T* __restrict__ o,
                                                              float* __restrict__ lse, int Hq, int D, int S,
                                                              int64_t osb, int64_t osh, const PeerScatter peer) {
+    __shared__ float sw[64];
     const int h = blockIdx.x, b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)b * Hq + h) * S;
     pdl_wait();                     // the split-KV grid before this one has completed and its partials are visible
-    float M = -INFINITY;
-    for (int s = 0; s < S; ++s) M = fmaxf(M, lse_part[row + s]);
-    float den = 0.f;
-    for (int s = 0; s < S; ++s) {
-        const float l = lse_part[row + s];
-        den += (l == -INFINITY) ? 0.f : __expf(l - M);
+    const float l0 = lane < S ? lse_part[row + lane] : -INFINITY;
+    const float l1 = lane + 32 < S ? lse_part[row + lane + 32] : -INFINITY;
+    float M = fmaxf(l0, l1);
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
+    const float w0 = l0 == -INFINITY ? 0.f : __expf(l0 - M);
+    const float w1 = l1 == -INFINITY ? 0.f : __expf(l1 - M);
+    float den = w0 + w1;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o2);
+    if (threadIdx.x < 32) {         // every warp computed the same weights; warp 0 publishes them
+        sw[lane] = w0;
+        sw[lane + 32] = w1;
     }
+    __syncthreads();
     const float inv = den > 0.f ? 1.f / den : 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float* src = o_part + row * D + d;
         float acc = 0.f;
-        for (int s = 0; s < S; ++s) {
-            const float l = lse_part[row + s];
-            const float w = (l == -INFINITY) ? 0.f : __expf(l - M);
-            acc = fmaf(w, o_part[(row + s) * D + d], acc);
+        int s = 0;
+        for (; s + 8 <= S; s += 8) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = src[(int64_t)(s + j) * D];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc = fmaf(sw[s + j], v[j], acc);
         }
+        for (; s < S; ++s) acc = fmaf(sw[s], src[(int64_t)s * D], acc);
         const T val = from_f32<T>(acc * inv);
         if (peer.n > 0) {
             const int64_t off = peer.base() + b * osb + h * osh + d;

@@ -213,7 +213,7 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
         it.q0[0] = slot * 2 * kBM;
         it.q0[1] = it.q0[0] + kBM;
     }
-    it.nk = p.seq_lens != nullptr ? p.seq_lens[it.b] : p.Nk;
+    it.nk = p.seq_lens != nullptr ? max(min(p.seq_lens[it.b], p.Nk), 0) : p.Nk;   // never past the host's bound (table width)
     it.nq = p.Nq;
     it.qbase = 0;
     it.bq = it.b;
@@ -397,7 +397,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     m_ref = m_new;
                     d *= alpha;
                 }
-                const float nmc = -m_ref * c;
+                // a row that has seen no visible key yet (seq_len < its query's position: a caller error the kernel
+                // survives) keeps m_ref = -inf: exponentiate against 0 so that P = 0 instead of NaN
+                const float nmc = m_ref == -INFINITY ? 0.f : -m_ref * c;
                 if (s > 0) {
                     sScale[(t * 2 + h) * 128 + row] = alpha;
                     if constexpr (kCorrCols > 0) sNmc[(t * 2 + h) * 128 + row] = nmc;
@@ -549,7 +551,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const float mlog2 = sMax[t * 128 + row];
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&stats_free[t]);
-                const float inv = 1.f / dsum;
+                const float inv = dsum > 0.f ? 1.f / dsum : 0.f;      // no visible key: O = 0, LSE = -inf
                 const int q_tile0 = it.q0[t];
                 // ragged tile of a packed q tensor: a TMA box would spill into the next sequence's rows, so the rows
                 // go from registers to global memory under a predicate (uniform over the 128 epilogue threads)

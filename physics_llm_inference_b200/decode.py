@@ -43,6 +43,7 @@ def flash_decode(
     workspace: torch.Tensor | None = None,
     out: torch.Tensor | None = None,
     peer_out=None,
+    validate: bool = False,
 ):
     """Attention of one query token per sequence over cached K/V.
 
@@ -51,6 +52,7 @@ def flash_decode(
               tensor (ragged batch; no host sync is made to read it)
     max_seq_len  host upper bound of seq_lens, used to pick the split count; defaults to the int
               seq_lens, else the cache length (contiguous) / table width * page size (paged)
+    validate  opt-in host check (one sync) of seq_lens / block-table ranges; off by default (no host sync)
     peer_out  a `sharding.PeerOutput`: q / caches are this rank's head shard; the kernel stores the shard's output
               into EVERY rank's full (B_total, Hq_total, D) buffer over NVLink and the call returns that full tensor
               once all ranks' slices have landed (fused all-gather, no NCCL call).
@@ -123,6 +125,12 @@ def flash_decode(
         if max_seq_len is None:
             max_seq_len = cap
     max_seq_len = min(int(max_seq_len), cap)
+    if validate:        # opt-in, one synchronising copy: the device-side preconditions (see validate_paged_args)
+        from .flash_attention import validate_paged_args
+        if paged:
+            validate_paged_args(lens, block_tables, bs, P, min_len=0, max_seq_len=max_seq_len)
+        elif int(lens.max()) > max_seq_len or int(lens.min()) < 0:
+            raise ValueError(f"seq_lens outside [0, {max_seq_len}]")
     if scale is None:
         scale = D ** -0.5
 
@@ -183,8 +191,9 @@ def _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_se
             ctypes.byref(ps), stream)
         _lib.check(rc)
         _lib.check(lib.pli_peer_publish_wait(ctypes.byref(ps), stream))
-    # under stream capture nothing ran yet: the caller accounts for replays with peer_out.advance()
-    o = peer_out.buffer((peer_out.epoch + 1) & 1) if torch.cuda.is_current_stream_capturing() else peer_out.advance()
+        # eager: the buffer of this step; under stream capture (nothing ran yet): the fixed `stable` tensor the captured
+        # step copies into — the caller accounts for replays with peer_out.advance(n)
+        o = peer_out.finish_step(ps, stream)
     return (o, lse) if return_lse else o
 
 

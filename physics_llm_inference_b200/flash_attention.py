@@ -44,6 +44,32 @@ def _unit_inner(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
+def validate_paged_args(seq_lens: torch.Tensor, block_tables: torch.Tensor, block_size: int, num_pages: int, *,
+                        q_lens=None, min_len: int = 1, max_seq_len: int | None = None) -> None:
+    """Opt-in (`validate=True`) host check of the DEVICE-side preconditions of the paged entry points; costs one
+    synchronising copy of the small index tensors.  The kernels themselves do not check them (no error can cross a
+    launch): seq_lens[b] in [max(q_len[b], min_len), table width * page size] and <= max_seq_len, and every block-table
+    entry a sequence uses inside [0, num_pages)."""
+    lens = seq_lens.detach().to("cpu", torch.int64)
+    table = block_tables.detach().to("cpu", torch.int64)
+    cap = table.shape[1] * block_size
+    bound = cap if max_seq_len is None else min(cap, int(max_seq_len))
+    if q_lens is None:
+        q_lens = torch.zeros_like(lens)
+    else:
+        q_lens = torch.as_tensor(q_lens, dtype=torch.int64).reshape(-1).expand(lens.shape[0]) if not torch.is_tensor(q_lens) \
+            else q_lens.detach().to("cpu", torch.int64)
+    for b in range(lens.shape[0]):
+        L, nq = int(lens[b]), int(q_lens[b])
+        if L < max(nq, min_len):
+            raise ValueError(f"sequence {b}: seq_len {L} is smaller than its {nq} query token(s) (rows without a visible key)")
+        if L > bound:
+            raise ValueError(f"sequence {b}: seq_len {L} exceeds the bound {bound} (block table width x page size, max_seq_len)")
+        used = table[b, :(L + block_size - 1) // block_size]
+        if used.numel() and (int(used.min()) < 0 or int(used.max()) >= num_pages):
+            raise ValueError(f"sequence {b}: a block-table entry in use is outside [0, {num_pages})")
+
+
 def _check_inputs(q, k, v):
     for name, x in (("q", q), ("k", k), ("v", v)):
         if not isinstance(x, torch.Tensor):
@@ -121,7 +147,7 @@ def flash_attention_forward(
                 sh.b_start, sh.q_start, ctypes.byref(ps), stream)
             _lib.check(rc)
             _lib.check(lib.pli_peer_publish_wait(ctypes.byref(ps), stream))
-        o = peer_out.buffer((peer_out.epoch + 1) & 1) if torch.cuda.is_current_stream_capturing() else peer_out.advance()
+            o = peer_out.finish_step(ps, stream)
         return (o, lse) if return_lse else o
     out = torch.empty_like(q)
     if out.stride(-1) != 1:
@@ -188,7 +214,7 @@ def prefill_algorithmic_flops(B: int, Hq: int, Nq: int, Nk: int, D: int, causal:
 
 def flash_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_tables: torch.Tensor,
                           seq_lens: torch.Tensor, *, layer: int = 0, scale: float | None = None,
-                          max_seq_len: int | None = None, return_lse: bool = False):
+                          max_seq_len: int | None = None, return_lse: bool = False, validate: bool = False):
     """Chunked prefill over the ch07 paged pools, read in place (no gather).
 
     q (B, Hq, Nq, D): the Nq newest tokens of each sequence (their K/V already appended to the pools, e.g. with
@@ -223,6 +249,8 @@ def flash_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.T
     max_seq_len = cap if max_seq_len is None else min(int(max_seq_len), cap)
     if Nq > max_seq_len:
         raise ValueError(f"Nq ({Nq}) exceeds the cached length bound ({max_seq_len})")
+    if validate:
+        validate_paged_args(seq_lens, block_tables, bs, P, q_lens=Nq, max_seq_len=max_seq_len)
     if scale is None:
         scale = D ** -0.5
     out = torch.empty_like(q)
@@ -242,7 +270,8 @@ def flash_attention_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.T
 
 def flash_attention_varlen_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_tables: torch.Tensor,
                                  seq_lens: torch.Tensor, cu_seqlens_q: torch.Tensor, max_q_len: int, *, layer: int = 0,
-                                 scale: float | None = None, max_seq_len: int | None = None, return_lse: bool = False):
+                                 scale: float | None = None, max_seq_len: int | None = None, return_lse: bool = False,
+                                 validate: bool = False):
     """`flash_attention_paged` for ragged query lengths: q (total_q, Hq, D) packs the newest tokens of every sequence,
     rows [cu_seqlens_q[b], cu_seqlens_q[b+1]) belong to sequence b (cu_seqlens_q (B+1,) int32 CUDA, max_q_len a host
     bound of the per-sequence lengths).  One launch serves the prefill side of a mixed batch
@@ -277,6 +306,13 @@ def flash_attention_varlen_paged(q: torch.Tensor, k_pool: torch.Tensor, v_pool: 
     q = _unit_inner(q)
     cap = block_tables.shape[1] * bs
     max_seq_len = cap if max_seq_len is None else min(int(max_seq_len), cap)
+    if validate:
+        cu = cu_seqlens_q.detach().to("cpu", torch.int64)
+        if int(cu[0]) != 0 or int(cu[-1]) != T or bool((cu[1:] < cu[:-1]).any()):
+            raise ValueError("cu_seqlens_q must be non-decreasing with [0] = 0 and [B] = total_q")
+        if int((cu[1:] - cu[:-1]).max()) > int(max_q_len):
+            raise ValueError(f"a sequence brings more than max_q_len = {max_q_len} query tokens")
+        validate_paged_args(seq_lens, block_tables, bs, P, q_lens=cu[1:] - cu[:-1], max_seq_len=max_seq_len)
     if scale is None:
         scale = D ** -0.5
     out = torch.empty((T, Hq, D), dtype=q.dtype, device=q.device)

@@ -16,13 +16,14 @@ from . import _lib
 
 
 def kv_append(k_store: torch.Tensor, v_store: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor,
-              start_pos, *, block_tables: torch.Tensor | None = None, layer: int = 0) -> None:
+              start_pos, *, block_tables: torch.Tensor | None = None, layer: int = 0, validate: bool = False) -> None:
     """Write k_new/v_new (B, n, Hkv, D) at positions start_pos[b] + i of each sequence.
 
     Contiguous storage (B, L, Hkv, D) when block_tables is None, else paged pools
     (P, layers, bs, Hkv, D) addressed through block_tables (B, max_pages) int32: token t goes to
     page block_tables[b, t // bs], slot t % bs (ch07/paged_memory.py:54,84-86).
-    start_pos: int or (B,) int32 device tensor.
+    start_pos: int or (B,) int32 device tensor.  An int start is bound-checked on the host; a device tensor is only
+    checked with validate=True (one synchronising copy): start_pos[b] + n must fit the cache / the table's pages.
     """
     if not (k_store.is_cuda and k_new.is_cuda):
         raise RuntimeError("kv_append runs on CUDA tensors only (no CPU fallback)")
@@ -59,6 +60,14 @@ def kv_append(k_store: torch.Tensor, v_store: torch.Tensor, k_new: torch.Tensor,
             raise RuntimeError("block_tables must be a CUDA int32 tensor with unit inner stride")
         st = k_store.stride()[:4]
         table_ptr, bs, tstride = block_tables.data_ptr(), k_store.shape[2], block_tables.stride(0)
+    capacity = k_store.shape[1] if block_tables is None else block_tables.shape[1] * k_store.shape[2]
+    if isinstance(start_pos, int):
+        if start_pos < 0 or start_pos + n > capacity:
+            raise RuntimeError(f"KV append of {n} token(s) at position {start_pos} does not fit the capacity {capacity}")
+    elif validate:
+        hi, lo = int(start.max()), int(start.min())
+        if lo < 0 or hi + n > capacity:
+            raise ValueError(f"KV append of {n} token(s) at positions [{lo}, {hi}] does not fit the capacity {capacity}")
     lib = _lib.load()
     with _lib.on_device(dev):
         rc = lib.pli_kv_append(k_new.data_ptr(), v_new.data_ptr(), k_store.data_ptr(), v_store.data_ptr(), table_ptr,

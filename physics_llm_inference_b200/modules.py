@@ -122,6 +122,10 @@ class DecodeGraphRunner:
         if not torch.cuda.is_available():
             return False
         start = seq_lens.to(device=self.seq_lens.device, dtype=torch.int32).clone()
+        # warm-up and capture append one token at position seq_lens[b]: it must exist (cache row / allocated page)
+        if int(start.max()) + 1 > self.capacity or int(start.min()) < 0:
+            raise RuntimeError(f"cannot capture a decode step at lengths up to {int(start.max())}: the cache holds "
+                               f"{self.capacity} tokens per sequence and the step appends one")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -83,10 +83,14 @@ def gather_heads(o_local: torch.Tensor, shard: HeadShard, group=None) -> torch.T
     if W == 1:
         return o_local
     x = o_local.contiguous()
-    buf = torch.empty((W, *x.shape), dtype=x.dtype, device=x.device)
+    # the flat collective wants the output as the concatenation along dim 0 (gloo insists on that shape)
+    flat = torch.empty((W * x.shape[0], *x.shape[1:]), dtype=x.dtype, device=x.device)
+    buf = flat.view(W, *x.shape)
     try:
-        dist.all_gather_into_tensor(buf, x, group=group)
-    except (RuntimeError, NotImplementedError):
+        dist.all_gather_into_tensor(flat, x, group=group)
+    except NotImplementedError:
+        # a backend without the flat collective (never NCCL): the list form.  A RuntimeError (an NCCL failure, a shape
+        # mismatch between ranks) is an error and propagates — it must not turn into a second, slower collective.
         parts = [torch.empty_like(x) for _ in range(W)]
         dist.all_gather(parts, x, group=group)
         buf = torch.stack(parts, 0)
@@ -112,8 +116,18 @@ class PeerOutput:
     overwrites data a slower peer is still reading (see include/pli_attention.h)."""
 
     def __init__(self, batch: int, num_heads: int, head_dim: int, dtype: torch.dtype, shard: HeadShard, *, group=None,
-                 device=None, seq_len: int | None = None):
-        """Output of a decode step (B, Hq, D), or with `seq_len` of a prefill call (B, Hq, seq_len, D)."""
+                 device=None, seq_len: int | None = None, graph_safe: bool = False):
+        """Output of a decode step (B, Hq, D), or with `seq_len` of a prefill call (B, Hq, seq_len, D).
+
+        graph_safe: also allocate a FIXED output tensor.  Under CUDA-graph capture the double buffer a replay writes
+        alternates with the device step counter, so a consumer captured in the same graph (o_proj, the next layer) would
+        read a stale buffer on every other replay; with graph_safe=True a captured step ends with a device-side copy
+        from the buffer of that step (parity read on the device) into `stable`, and the call returns `stable`.  Capturing
+        a step without it raises.  Costs one extra output-sized buffer and one pass over it per captured step.
+
+        Stream contract: every kernel that reads the output of step e must be enqueued on the stream that issues step
+        e + 1 (or be ordered before it by an event): a rank passes the flag wait of step e + 1 only after all peers have
+        run, in stream order, the readers of step e — that is what makes two buffers enough."""
         if shard.world_size > 8:
             raise ValueError("PeerOutput supports up to 8 ranks (one NVSwitch domain)")
         self.shard, self.dtype = shard, dtype
@@ -121,6 +135,8 @@ class PeerOutput:
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.esz = torch.empty((), dtype=dtype).element_size()
         self.numel = batch * num_heads * head_dim * (1 if seq_len is None else seq_len)
+        if (self.numel * self.esz) % 16:
+            raise ValueError("PeerOutput needs an output of a multiple of 16 bytes")
         self.buf_bytes = -(-self.numel * self.esz // 256) * 256
         self.header_bytes = 512
         total = self.header_bytes + 2 * self.buf_bytes
@@ -138,6 +154,23 @@ class PeerOutput:
             self.handle = None
             self.base_ptrs = [self.storage.data_ptr()]
         self.epoch = 0                                        # host mirror of the device step counter
+        self.stable = torch.empty(self.shape, dtype=dtype, device=self.device) if graph_safe else None
+
+    def finish_step(self, ps, stream: int) -> torch.Tensor:
+        """Called by the fused entry points after pli_peer_publish_wait: the tensor the caller gets for this step."""
+        from . import _lib
+        if not torch.cuda.is_current_stream_capturing():
+            _lib.raise_on_device_fault()                      # e.g. a peer that never arrived in an EARLIER step
+            return self.advance()
+        if self.stable is None:
+            raise RuntimeError(
+                "a fused-gather step is being captured in a CUDA graph, but this PeerOutput has no fixed output: the "
+                "double buffer a replay writes alternates with the step parity.  Build it with PeerOutput(..., "
+                "graph_safe=True) (the captured step then copies into `.stable`), and call advance(n) after replays")
+        import ctypes
+        _lib.check(_lib.load().pli_peer_select_copy(ctypes.byref(ps), self.stable.data_ptr(), self.numel * self.esz,
+                                                    self.esz, stream))
+        return self.stable
 
     def buffer(self, index: int) -> torch.Tensor:
         """This rank's copy of output buffer `index`, shaped (B, Hq, D) or (B, Hq, N, D)."""

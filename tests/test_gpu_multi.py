@@ -48,21 +48,38 @@ def _worker(rank, world, port, out_dir):
     kw = dict(block_tables=table, max_seq_len=max(lens_l))
     ref = pli.gather_heads(pli.flash_decode(qs, kps, vps, lens, **kw)[:, :, 0], shard)
     ws = pli.decode_workspace(qs.shape[0], qs.shape[1], D, pli.decode_num_splits(qs.shape[0], kps.shape[3], max(lens_l)), dev)
+    # ONE step per graph (an odd count: the double buffer a replay writes alternates), with a CONSUMER captured in the
+    # same graph (stands for o_proj / the next layer): it must see the step's output on every replay, which needs the
+    # fixed `stable` tensor of a graph_safe PeerOutput (the alternating buffer was returned here before)
+    try:
+        with torch.cuda.graph(torch.cuda.CUDAGraph()):
+            pli.flash_decode(qs, kps, vps, lens, peer_out=po, workspace=ws, **kw)
+        ok, why = False, "capturing a step of a PeerOutput without graph_safe=True did not raise"
+    except RuntimeError:
+        pass
+    torch.cuda.synchronize()
+    dist.barrier()
+    pog = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard, graph_safe=True)
+    consumed = torch.zeros(B, Hq, D, device=dev, dtype=torch.float32)
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.stream(side):
-        pli.flash_decode(qs, kps, vps, lens, peer_out=po, workspace=ws, **kw)          # warm-up outside the graph
+        pli.flash_decode(qs, kps, vps, lens, peer_out=pog, workspace=ws, **kw)         # warm-up outside the graph
         torch.cuda.synchronize()
         with torch.cuda.graph(graph):
-            pli.flash_decode(qs, kps, vps, lens, peer_out=po, workspace=ws, **kw)
+            og = pli.flash_decode(qs, kps, vps, lens, peer_out=pog, workspace=ws, **kw)
+            consumed.copy_(og.float() * 2)
     torch.cuda.current_stream(dev).wait_stream(side)
-    for rep in range(3):
+    for rep in range(5):
+        consumed.zero_()
         graph.replay()
-        o = po.advance()
+        o = pog.advance()
         torch.cuda.synchronize()
         if not torch.equal(o, ref):
             ok, why = False, f"graph replay {rep}: fused != gathered"
+        if not torch.equal(consumed, ref.float() * 2):
+            ok, why = False, f"graph replay {rep}: the consumer captured in the graph read a stale buffer"
     # prefill: O tiles TMA-stored into every rank's full output
     Bp, N = 2, 640
     qf, kf, vf = orc.seeded_qkv(43, Bp, Hq, Hkv, N, N, D)

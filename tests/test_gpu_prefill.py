@@ -449,3 +449,31 @@ def test_expanded_zero_stride_views():
                                      torch.cuda.current_stream().cuda_stream)
     assert rc == 0
     assert (out.float() - ref.float()).abs().max().item() <= 2e-2
+
+
+def test_rows_without_a_visible_key_give_zero_output_and_minus_inf_lse():
+    """A caller error the kernels survive: seq_lens[b] < Nq leaves the first Nq - seq_lens[b] query rows
+    of that sequence with no visible key.  They come out as O = 0, LSE = -inf (not NaN), the other rows are unaffected,
+    and `validate=True` reports the violation on the host instead."""
+    bs, D, Hkv, G, Nq = 16, 128, 2, 4, 64
+    lens = [200, 40]                                   # sequence 1 is shorter than its 64 query tokens
+    _, kp, vp, table, lens_t = orc.seeded_paged(95, 2, Hkv * G, Hkv, D, bs, lens, dtype=torch.bfloat16)
+    q = torch.randn(2, Hkv * G, Nq, D, generator=torch.Generator().manual_seed(96)).bfloat16()
+    o, lse = pli.flash_attention_paged(q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens_t.cuda(), return_lse=True,
+                                       max_seq_len=max(lens))
+    dead = Nq - lens[1]
+    assert torch.count_nonzero(o[1, :, :dead]) == 0 and bool(torch.isinf(lse[1, :, :dead]).all()) and bool((lse[1, :, :dead] < 0).all())
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse[1, :, dead:]).all() and torch.isfinite(lse[0]).all()
+    ro, rl = orc.paged_decode_oracle(q[:1], kp, vp, table[:1], lens_t[:1])
+    assert (o[:1].float().cpu() - ro).abs().max().item() <= 2e-2
+    # live rows of the short sequence: query i (i >= dead) sees keys j <= i - dead
+    ro1, _ = orc.paged_decode_oracle(q[1:, :, dead:], kp, vp, table[1:], lens_t[1:])
+    assert (o[1:, :, dead:].float().cpu() - ro1).abs().max().item() <= 2e-2
+    with pytest.raises(ValueError):
+        pli.flash_attention_paged(q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens_t.cuda(), validate=True)
+    bad = table.clone()
+    bad[0, 1] = kp.shape[0] + 7
+    with pytest.raises(ValueError):
+        pli.flash_decode(q[:, :, :1].cuda(), kp.cuda(), vp.cuda(), lens_t.cuda(), block_tables=bad.cuda(), validate=True)
+    with pytest.raises(RuntimeError):
+        pli.kv_append(kp.cuda(), vp.cuda(), kp[:2, 0, :4].cuda(), vp[:2, 0, :4].cuda(), 10 ** 6, block_tables=table.cuda())
