@@ -48,6 +48,8 @@ inline cudaError_t ensure_dynamic_smem(Kern kern, int bytes) {
 // thread, [2] detail (barrier shared-memory address | parity << 32, or peer rank << 32 | step), [3] %globaltimer.
 unsigned long long* status_words();
 uint64_t peer_timeout_ns();
+cudaError_t bind_status_prefill();   // prefill_tcgen05.cu
+cudaError_t bind_status_decode();    // decode.cu
 #define PLI_FAULT_NONE 0
 #define PLI_FAULT_MBARRIER_TIMEOUT 1   /* an intra-kernel mbarrier wait exceeded PLI_MBAR_TIMEOUT_NS: protocol bug; the kernel traps */
 #define PLI_FAULT_PEER_TIMEOUT 2       /* a peer rank's slice did not arrive within the peer timeout: reported, NOT trapped */
@@ -180,8 +182,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     }
 }
 
-// host side of the fault record: bind this translation unit's c_pli_status on the current device (once per device)
-inline cudaError_t bind_status_symbol() {
+// host side of the fault record: bind THIS translation unit's c_pli_status on the current device (once per device and
+// unit: the function and its bitmask are static, like the symbol).  pli_set_device binds every unit up front (a
+// cudaMemcpyToSymbol is not allowed while a stream is capturing); the launchers call it again as a cheap fallback.
+static inline cudaError_t bind_status_symbol() {
     static thread_local uint64_t bound = 0;
     const int dev = current_device();
     if (dev >= 0 && dev < 64 && ((bound >> dev) & 1)) return cudaSuccess;

@@ -459,18 +459,22 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
 // S <= 64) instead of three serial passes over them, the weights go through shared memory, and the weighted sum over the
 // partial outputs keeps eight independent, coalesced loads in flight per thread: with few sequences and many splits
 // (B1 x L32768: 37 splits) the old serial loops cost more than the split-KV kernel they followed.
+//
+// The partials are written by the grid this one is programmatically launched behind: every read of them must stay BEHIND
+// griddepcontrol.wait.  They are therefore NOT `const __restrict__` (loads through such pointers are "invariant" and the
+// compiler hoisted them above the wait: LDG.E.CONSTANT in front of ACQBULK in the SASS, stale partials for the CTAs that
+// were still running — caught by test_paged_decode_tma) and go through ld.global.cg.
 template <typename T>
-__global__ void __launch_bounds__(128) decode_combine_kernel(const float* __restrict__ o_part,
-                                                             const float* __restrict__ lse_part, T* __restrict__ o,
-                                                             float* __restrict__ lse, int Hq, int D, int S,
-                                                             int64_t osb, int64_t osh, const PeerScatter peer) {
+__global__ void __launch_bounds__(128) decode_combine_kernel(const float* o_part, const float* lse_part, T* o, float* lse,
+                                                             int Hq, int D, int S, int64_t osb, int64_t osh,
+                                                             const PeerScatter peer) {
     __shared__ float sw[64];
     const int h = blockIdx.x, b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int64_t row = ((int64_t)b * Hq + h) * S;
     pdl_wait();                     // the split-KV grid before this one has completed and its partials are visible
-    const float l0 = lane < S ? lse_part[row + lane] : -INFINITY;
-    const float l1 = lane + 32 < S ? lse_part[row + lane + 32] : -INFINITY;
+    const float l0 = lane < S ? __ldcg(lse_part + row + lane) : -INFINITY;
+    const float l1 = lane + 32 < S ? __ldcg(lse_part + row + lane + 32) : -INFINITY;
     float M = fmaxf(l0, l1);
 #pragma unroll
     for (int o2 = 16; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
@@ -492,11 +496,11 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const float* __rest
         for (; s + 8 <= S; s += 8) {
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = src[(int64_t)(s + j) * D];
+            for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + (int64_t)(s + j) * D);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc = fmaf(sw[s + j], v[j], acc);
         }
-        for (; s < S; ++s) acc = fmaf(sw[s], src[(int64_t)s * D], acc);
+        for (; s < S; ++s) acc = fmaf(sw[s], __ldcg(src + (int64_t)s * D), acc);
         const T val = from_f32<T>(acc * inv);
         if (peer.n > 0) {
             const int64_t off = peer.base() + b * osb + h * osh + d;
@@ -651,6 +655,9 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
 }
 
 }  // namespace
+
+cudaError_t bind_status_decode() { return bind_status_symbol(); }
+
 }  // namespace pli
 
 using namespace pli;

@@ -126,6 +126,8 @@ extern "C" int pli_set_device(int device) {
     PLI_CUDA_CHECK(cudaSetDevice(device));
     g_device = device;
     if (!device_is_sm100()) return set_error(PLI_ERR_DEVICE, "CUDA device %d is not sm_100 (B200)", device);
+    PLI_CUDA_CHECK(bind_status_prefill());       // the fault record's device-side pointer, per translation unit
+    PLI_CUDA_CHECK(bind_status_decode());
     return PLI_OK;
 }
 extern "C" int pli_device_status(uint64_t out[8], int clear) {

@@ -1835,6 +1835,8 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
 #undef PLI_GO
 }
 
+cudaError_t bind_status_prefill() { return bind_status_symbol(); }
+
 }  // namespace pli
 
 using namespace pli;

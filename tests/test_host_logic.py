@@ -244,3 +244,31 @@ def test_share_prefix_from_a_radix_hit_is_page_granular(golden_dir):
     assert all(p not in cache.free_blocks for p in r["pages_a"][:3])             # still referenced by request 2
     cache.free_blocks_for_request(2)
     assert cache.get_num_free_blocks() == 32 and not cache.shared_refs
+
+
+def test_combine_pass_reads_partials_only_behind_the_dependency_wait():
+    """The split-KV combine kernel is launched programmatically behind the kernel that writes the partials: in its SASS
+    no global load may precede ACQBULK (griddepcontrol.wait).  Round 2 found `const __restrict__` loads hoisted above the
+    wait (stale partials); this disassembles the built library so the regression shows up without a GPU."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "decode_combine_kernel", _lib.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode != 0 or "Function" not in sass.stdout:
+        sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True)
+    kernels, cur = {}, None
+    for line in sass.stdout.splitlines():
+        if "Function :" in line:
+            cur = line.split("Function :")[1].strip() if "decode_combine_kernel" in line else None
+            if cur:
+                kernels[cur] = []
+        elif cur and "/*" in line:
+            kernels[cur].append(line)
+    assert len(kernels) >= 3, "combine kernel instantiations not found in the library"
+    for name, lines in kernels.items():
+        wait = next((i for i, l in enumerate(lines) if "ACQBULK" in l), None)
+        assert wait is not None, f"{name}: no griddepcontrol.wait (ACQBULK)"
+        early = [l for l in lines[:wait] if " LDG" in l or "LD.E" in l]
+        assert not early, f"{name}: global loads in front of the dependency wait:\n" + "\n".join(early)
