@@ -165,6 +165,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same, for waiters that are off the critical path (correction warps, TMA producer): a suspend-time hint
 // lets the hardware park the warp for up to ~1 us per probe instead of re-polling every ~50 cycles, which
 // matters on a power-capped part.
+template <uint32_t kSuspendNs = 1000>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     uint64_t t0 = 0;
@@ -175,7 +176,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, P;\n\t}\n"
             : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendNs)
             : "memory");
         if (ok) return;
         if ((++spins & 0xFFFu) == 0) mbar_watchdog(t0, bar, parity);     // a probe parks the warp for up to ~1 us
@@ -265,6 +266,61 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
         "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
             reinterpret_cast<uint64_t>(map)),
         "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+// ---- the same with an L2 eviction-priority hint (createpolicy encodings): Q tiles and O tiles are touched once
+// (evict first), K/V tiles are re-read by every Q tile of their KV group (evict last) ----
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_hint(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                      int c0, int c1, int c2, int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_multicast_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                                           int c1, int c2, int c3, uint16_t cta_mask, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7, %8;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask),
+        "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                 int c2, int c3, int c4, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_multicast_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                                           int c1, int c2, int c3, int c4, uint16_t cta_mask,
+                                                           uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8, %9;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+        "h"(cta_mask), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;\n" ::"l"(
+            reinterpret_cast<uint64_t>(map)),
+        "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }

@@ -47,6 +47,19 @@ constexpr int kPolyPairs = PLI_POLY_PAIRS;   // of every 16 element pairs, how m
 #define PLI_CORR_COLS 16
 #endif
 constexpr int kCorrCols = PLI_CORR_COLS;
+// L2 eviction hints on the TMA traffic of the product kernel: Q and O tiles evict-first (touched once), K/V evict-last
+// (re-read by every Q tile of the KV group).  Round 1 measured 1.09 GB of DRAM traffic per C2 launch against 0.67 GB
+// algorithmic: the streamed 0.5 GB of Q and O pushed K/V out of L2.
+#ifndef PLI_L2_HINTS
+#define PLI_L2_HINTS 1
+#endif
+#ifndef PLI_DIRECT_EPILOGUE
+#define PLI_DIRECT_EPILOGUE 0
+#endif
+constexpr bool kDirectEpilogue = PLI_DIRECT_EPILOGUE != 0;
+constexpr uint64_t kHintQ = PLI_L2_HINTS ? kL2EvictFirst : 0x1000000000000000ull;    // else: evict-normal
+constexpr uint64_t kHintKV = PLI_L2_HINTS ? kL2EvictLast : 0x1000000000000000ull;
+constexpr uint64_t kHintO = PLI_L2_HINTS ? kL2EvictFirst : 0x1000000000000000ull;
 static_assert(kCorrCols == 0 || kCorrCols == 16 || kCorrCols == 32, "kCorrCols: 0, 16 or 32 of the 64 columns");
 #ifndef PLI_PROFILE
 #define PLI_PROFILE 0                     // 1: compile the in-kernel timeline / phase counters (tuning builds only)
@@ -79,6 +92,30 @@ struct SmemLayout {
     static constexpr int kTotal = kTmemPtrOff + 16;
 };
 
+// Division by a run-time constant as multiply-high + shift (the multiplier is found on the host: ceil(2^p / d) with
+// p = 31 + ceil(log2 d); exact for dividends below 2^31).  decode_item runs once per work item in EVERY warp role, and
+// its six integer divisions, each a ~150-cycle dependent chain on a GPU without a divider, were ~1500 serial cycles per
+// item and role (in-kernel timeline at N = 512: every role idled that long between items).
+struct FastDiv {
+    uint32_t d, mul, sh;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> sh); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d ? d : 1u, 0u, 0u};
+    if (f.d > 1) {
+        uint32_t l = 0;
+        while ((1ull << l) < f.d) ++l;
+        const uint32_t pw = 31 + l;
+        f.mul = (uint32_t)(((1ull << pw) + f.d - 1) / f.d);
+        f.sh = pw - 32;
+    }
+    return f;
+}
+
 struct PrefillParams {
     float* lse;
     int B, Hq, Hkv, Nq, Nk;
@@ -95,6 +132,10 @@ struct PrefillParams {
     int trace_cap;
     int debug_flags;             // bit 0: skip the exp2 / P computation (timing experiments only)
     int pair_block;              // scheduling block (see decode_item)
+    // decode_item's divisors: items per block, per (group x slots) of a full / of the last (short) block, per (group, slot),
+    // kv heads; and G = Hq / Hkv
+    FastDiv fd_block, fd_group_full, fd_group_last, fd_gi, fd_hkv;
+    int group, cnt_last;
     // paged K/V (kPaged kernels): keys of sequence b come from the pools through its block-table row; Nk is then
     // per sequence (seq_lens[b]) and the mask is bottom-right aligned per sequence
     const int32_t* table;
@@ -104,7 +145,7 @@ struct PrefillParams {
     // to sequence b; Nq is then the host's upper bound of the per-sequence lengths (it sizes the schedule)
     const int32_t* cu_q;
     uint8_t* o_base;                  // raw o pointer + element strides for the predicated store of ragged tiles
-    int64_t o_st_tok, o_st_head;
+    int64_t o_st_tok, o_st_head, o_st_batch;
     int64_t lse_sb, lse_sh;           // lse index = b * lse_sb + h * lse_sh + (row inside the q tensor)
 };
 
@@ -133,6 +174,22 @@ __device__ __forceinline__ void trace_event(const PrefillParams& p, int lane, in
 }
 
 constexpr int kHN = 64;                // keys per softmax / MMA half-step (half of a KV tile)
+
+// O_t row *= alpha in tensor memory (the rare half-steps in which the running maximum grew by more than 2^8).  Out of
+// line on purpose: inlined, its four LDTM / 32 FMUL / STTM groups sat between the hot blocks of the correction loop and
+// every pass jumped over ~2.6 KB of cold code twice (instruction-fetch stalls after the taken branches).
+template <int kD>
+__device__ __noinline__ void rescale_o_rows(uint32_t o_addr, float alpha) {
+#pragma unroll
+    for (int ch = 0; ch < kD / 32; ++ch) {
+        float orr[32];
+        tmem_ld_x32(o_addr + ch * 32, orr);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) orr[i] *= alpha;
+        tmem_st_x32(o_addr + ch * 32, orr);
+    }
+}
 
 // P = exp2(S * c - m * c) for 16 scores of a row: packed FFMA2 for the argument, MUFU.EX2 (an FMA-pipe polynomial for
 // kPolyPairs of every 16 pairs), row sums in two packed FADD2 chains, bf16/f16 pairs packed into pk[0..8).
@@ -190,26 +247,25 @@ __device__ __forceinline__ WorkItem decode_item(int w, const PrefillParams& p) {
     // blocks of 1, 1.2 GB for 2, 0.65 GB for 4; measured +2 %); item sizes inside a block differ by
     // < pair_block slots, so the snake schedule still balances.  Consecutive items (even, odd) are the same
     // slot of the same KV group whenever the per-group item count is even: that is what CTA pairs rely on.
+    // All divisions are by launch constants (FastDiv).
     WorkItem it;
-    const int kPairBlock = p.pair_block;
-    const int G = p.Hq / p.Hkv;
-    const int Gi = p.head_pairs ? G / 2 : G;                       // items per (KV group, slot)
-    const int per_slot = p.B * p.Hkv * Gi;
-    const int blk = w / (kPairBlock * per_slot);
-    int r = w - blk * kPairBlock * per_slot;
-    const int top = p.num_pairs - 1 - blk * kPairBlock;           // largest slot index of this block
-    const int cnt = min(kPairBlock, top + 1);                      // slots in this block (the last one may be short)
-    const int g = r / (cnt * Gi);
-    r -= g * cnt * Gi;
-    const int slot = top - r / Gi;
-    it.b = g / p.Hkv;
-    it.hk = g % p.Hkv;
+    const int G = p.group;
+    uint32_t blk, r, g, sl, gi, b, hk;
+    p.fd_block.divmod((uint32_t)w, blk, r);                        // block of pair_block slots, index inside it
+    const int top = p.num_pairs - 1 - (int)blk * p.pair_block;     // largest slot index of this block
+    if (top + 1 >= p.pair_block) p.fd_group_full.divmod(r, g, r);  // KV group; (slot, item) inside the group
+    else p.fd_group_last.divmod(r, g, r);                          // the last block may be short (cnt_last slots)
+    p.fd_gi.divmod(r, sl, gi);
+    const int slot = top - (int)sl;
+    p.fd_hkv.divmod(g, b, hk);
+    it.b = (int)b;
+    it.hk = (int)hk;
     if (p.head_pairs) {
-        it.h[0] = it.hk * G + (r % Gi) * 2;
+        it.h[0] = it.hk * G + (int)gi * 2;
         it.h[1] = it.h[0] + 1;
         it.q0[0] = it.q0[1] = slot * kBM;
     } else {
-        it.h[0] = it.h[1] = it.hk * G + r % Gi;
+        it.h[0] = it.h[1] = it.hk * G + (int)gi;
         it.q0[0] = slot * 2 * kBM;
         it.q0[1] = it.q0[0] + kBM;
     }
@@ -359,7 +415,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const int nt = it.n[t];
             float m_ref = -INFINITY;                      // reference max (raw score units)
             float d = 0.f;                                // running row sum relative to m_ref
-            for (int s = 0; s < nt; ++s) {
+            // One half-step.  kInterior = true is the hot instance: s >= 1 and no key of the half-step is masked for any row
+            // of the tile, so neither the mask code nor the first-step special cases are in its instruction stream (they
+            // used to sit in the middle of the loop and cost instruction-fetch stalls: ncu showed ~5 % no_inst + ~5 %
+            // branch_resolving samples in these warps); the cold instance serves step 0 and the masked steps, which are
+            // always the LAST ones of an item (key padding, causal diagonal).
+            auto half_step = [&](const int s, auto interior_tag) {
+                constexpr bool kInterior = decltype(interior_tag)::value;
                 const int h = s & 1;
                 const uint32_t s_addr = tmem_base + t * 128 + h * 64 + lane_addr;
                 mbar_wait(&s_full[t * 2 + h], (sf_par >> h) & 1);
@@ -371,14 +433,16 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tmem_ld_x32(s_addr + 32, sv + 32);
                 tc_wait_ld();
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 6, t, s);       // S in registers
-                // mask: key padding and the causal diagonal (warp-uniform test, per-row limit)
-                const int k0 = s * kHN;
-                const bool need_mask = (k0 + kHN > nk) || (p.causal && (k0 + kHN - 1 > q_tile0 + off));
-                if (need_mask) {
-                    int vis = nk - 1 - k0;
-                    if (p.causal) vis = min(vis, q_row + off - k0);
+                if constexpr (!kInterior) {
+                    // mask: key padding and the causal diagonal (warp-uniform test, per-row limit)
+                    const int k0 = s * kHN;
+                    const bool need_mask = (k0 + kHN > nk) || (p.causal && (k0 + kHN - 1 > q_tile0 + off));
+                    if (need_mask) {
+                        int vis = nk - 1 - k0;
+                        if (p.causal) vis = min(vis, q_row + off - k0);
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
+                        for (int i = 0; i < 64; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
+                    }
                 }
                 float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
@@ -390,7 +454,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
                 float alpha = 1.f;
-                if (s == 0) {
+                if (!kInterior && s == 0) {
                     m_ref = m_new;                        // first half-step: nothing accumulated yet
                 } else if ((m_new - m_ref) * c > kRescaleThreshold) {
                     alpha = ex2_approx((m_ref - m_new) * c);
@@ -400,7 +464,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // a row that has seen no visible key yet (seq_len < its query's position: a caller error the kernel
                 // survives) keeps m_ref = -inf: exponentiate against 0 so that P = 0 instead of NaN
                 const float nmc = m_ref == -INFINITY ? 0.f : -m_ref * c;
-                if (s > 0) {
+                if (kInterior || s > 0) {
                     sScale[(t * 2 + h) * 128 + row] = alpha;
                     if constexpr (kCorrCols > 0) sNmc[(t * 2 + h) * 128 + row] = nmc;
                     __syncwarp();
@@ -412,19 +476,19 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const float2 c2 = make_float2(c, c);
                 const float2 nmc2 = make_float2(nmc, nmc);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-                const int n_chunks = s > 0 ? (kHN - kCorrCols) / 16 : 4;                // warp-uniform
+                const int n_chunks = (kInterior || s > 0) ? (kHN - kCorrCols) / 16 : 4;   // warp-uniform
                 {
                     uint32_t pk[16];
                     exp_chunk16<kBf16>(sv + 0, c2, nmc2, acc0, acc1, pk);
                     exp_chunk16<kBf16>(sv + 16, c2, nmc2, acc0, acc1, pk + 8);
                     tmem_st_x16(s_addr, pk);
                 }
-                if (kCorrCols < 32 || n_chunks > 2) {
+                if (kCorrCols < 32 || (!kInterior && n_chunks > 2)) {
                     uint32_t pk[8];
                     exp_chunk16<kBf16>(sv + 32, c2, nmc2, acc0, acc1, pk);
                     tmem_st_x8(s_addr + 16, pk);
                 }
-                if (kCorrCols < 16 || n_chunks > 3) {
+                if (kCorrCols < 16 || (!kInterior && n_chunks > 3)) {
                     uint32_t pk[8];
                     exp_chunk16<kBf16>(sv + 48, c2, nmc2, acc0, acc1, pk);
                     tmem_st_x8(s_addr + 24, pk);
@@ -437,6 +501,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 __syncwarp();
                 if (lane == 0) arrive_pv_ok(t * 2 + h);
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 3, t, s);       // P posted
+            };
+            // half-steps [1, n_plain) are interior: 64 (s + 1) <= nk and, when causal, 64 s + 63 <= q_tile0 + off
+            int n_plain = min(nt, nk / kHN);
+            if (p.causal) n_plain = min(n_plain, q_tile0 + off - (kHN - 1) >= 0 ? (q_tile0 + off - (kHN - 1)) / kHN + 1 : 0);
+            for (int s = 0; s < nt; ++s) {
+                if (s >= 1 && s < n_plain) half_step(s, std::true_type{});
+                else half_step(s, std::false_type{});
             }
             mbar_wait(&stats_free[t], item_par ^ 1);      // previous item's epilogue has read the slots
             sSum[t * 128 + row] = d;
@@ -520,15 +591,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             mbar_wait(&pv_tail[t], item_cnt & 1);
                         }
                         tc_fence_after();
-#pragma unroll
-                        for (int ch = 0; ch < kD / 32; ++ch) {
-                            float orr[32];
-                            tmem_ld_x32(tmem_base + 256 + t * 128 + lane_addr + ch * 32, orr);
-                            tc_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) orr[i] *= alpha;
-                            tmem_st_x32(tmem_base + 256 + t * 128 + lane_addr + ch * 32, orr);
-                        }
+                        rescale_o_rows<kD>(tmem_base + 256 + t * 128 + lane_addr, alpha);
                         tc_wait_st();
                         tc_fence_before();
                     } else if constexpr (kCorrCols > 0) {
@@ -543,6 +606,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             // ---- epilogue: O_t / d -> bf16 -> swizzled smem -> TMA store; LSE ----
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
+                if (wq == 0) trace_event(p, lane, 4, trace_cur, 10, t, 0);                // epilogue of tile t starts
                 mbar_wait_relaxed(&stats_full[t], item_cnt & 1);
                 mbar_wait_relaxed(&o_final[t], item_cnt & 1);
                 mbar_wait_relaxed(&pv_tail[t], item_cnt & 1);         // one phase per item: keeps its parity in step
@@ -557,6 +621,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // go from registers to global memory under a predicate (uniform over the 128 epilogue threads)
                 bool direct = false;
                 if constexpr (kPaged) direct = p.cu_q != nullptr && q_tile0 + kBM > it.nq;
+                // Every tile straight from the registers (no shared-memory staging, no TMA store, no CTA-wide barriers)
+                // when the output is local: the staged path serialises four named barriers and two waits for the
+                // previous TMA store's shared-memory read per tile, which is what short items are made of.
+                if (kDirectEpilogue && p.o_base != nullptr && peers.n == 0) direct = true;
 #pragma unroll
                 for (int hf = 0; hf < kHalves; ++hf) {
                     // the previous TMA store must have finished reading sO before it is overwritten
@@ -578,9 +646,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                         uint8_t* srow = sO + row * 128;
                         uint8_t* grow = nullptr;
-                        if constexpr (kPaged) {
+                        if constexpr (kPaged || kDirectEpilogue) {
                             if (direct && q_tile0 + row < it.nq)
-                                grow = p.o_base + ((int64_t)(it.qbase + q_tile0 + row) * p.o_st_tok +
+                                grow = p.o_base + ((int64_t)it.bq * p.o_st_batch + (int64_t)(it.qbase + q_tile0 + row) * p.o_st_tok +
                                                    (int64_t)it.h[t] * p.o_st_head + ch * 32) * 2;
                         }
 #pragma unroll
@@ -600,7 +668,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         named_bar_sync(kBarEpilogue, 128);
                         if (warp == 8 && lane == 0 && q_tile0 < it.nq) {
                             if (kPaged || peers.n == 0) {
-                                tma_store_4d(&map_o, sO, hf * 64, it.qbase + q_tile0, it.h[t], it.bq);
+                                tma_store_4d_hint(&map_o, sO, hf * 64, it.qbase + q_tile0, it.h[t], it.bq, kHintO);
                             } else {
                                 for (int r = 0; r < peers.n; ++r)
                                     tma_store_4d(&peers.maps[peer_buf][r], sO, hf * 64, q_tile0, it.h[t] + peers.head_offset,
@@ -610,6 +678,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                     }
                 }
+                if (wq == 0) trace_event(p, lane, 4, trace_cur, 11, t, 0);                // epilogue of tile t done
                 if (p.lse != nullptr && q_tile0 + row < it.nq)
                     p.lse[it.b * p.lse_sb + it.h[t] * p.lse_sh + it.qbase + q_tile0 + row] = (mlog2 + log2f(dsum)) * kLn2;
                 // s_full[t*2+h] completed ceil((n_t - h) / 2) phases in this item
@@ -695,6 +764,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 mbar_wait(&q_full[t], item_par);
                 wait_kv(0);
                 tc_fence_after();
+                trace_event(p, lane, 2 + t, trace_cur, 12, t, 0);                           // Q and the first K tile landed
                 if (elect_one()) {
                     issue_S(0, slot_of(0));
                     after_S(0);
@@ -778,20 +848,24 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const WorkItem it = decode_item(w, p);
                 auto load_q = [&](int t) {
                     if (lane == 0 && do_k) {
+#if defined(PLI_PRODUCER_SPIN) && PLI_PRODUCER_SPIN
+                        mbar_wait(&q_empty[t], item_par ^ 1);          // once per item, and the next item starts behind it
+#else
                         mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
+#endif
                         if constexpr (kPairMma) {
                             // both CTAs' Q tiles are counted by the leader's barrier (its MMA warp issues for the pair)
                             if (rank == 0) mbar_arrive_expect_tx(&q_full[t], 2 * kTileBytes);
 #pragma unroll
                             for (int hf = 0; hf < kHalves; ++hf)
-                                tma_load_4d_pair(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, q_full_leader + t * 8,
-                                                 hf * 64, it.qbase + it.q0[t], it.h[t], it.bq);
+                                tma_load_4d_pair_hint(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, q_full_leader + t * 8,
+                                                      hf * 64, it.qbase + it.q0[t], it.h[t], it.bq, kHintQ);
                         } else {
                             mbar_arrive_expect_tx(&q_full[t], kTileBytes);
 #pragma unroll
                             for (int hf = 0; hf < kHalves; ++hf)
-                                tma_load_4d(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
-                                            it.qbase + it.q0[t], it.h[t], it.bq);
+                                tma_load_4d_hint(sQ + t * kTileBytes + hf * kSubTileBytes, &map_q, &q_full[t], hf * 64,
+                                                 it.qbase + it.q0[t], it.h[t], it.bq, kHintQ);
                         }
                     }
                 };
@@ -825,10 +899,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             for (int hf = 0; hf < kHalves; ++hf)
 #pragma unroll
                                 for (int hh = 0; hh < 2; ++hh)
-                                    tma_load_4d_pair(dst + hf * (kSubTileBytes / 2) + hh * (32 * 128), map, bar, hf * 64,
-                                                     j * kBN + hh * kHN + rank * 32, it.hk, it.b);
+                                    tma_load_4d_pair_hint(dst + hf * (kSubTileBytes / 2) + hh * (32 * 128), map, bar, hf * 64,
+                                                          j * kBN + hh * kHN + rank * 32, it.hk, it.b, kHintKV);
                         } else {
-                            tma_load_4d_pair(dst, map, bar, rank * 64, j * kBN, it.hk, it.b);
+                            tma_load_4d_pair_hint(dst, map, bar, rank * 64, j * kBN, it.hk, it.b, kHintKV);
                         }
                         ++kv_cnt;
                         return;
@@ -843,9 +917,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                             for (int hf = 0; hf < kHalves; ++hf) {
                                 uint8_t* dst = sKV + slot * kTileBytes + hf * kSubTileBytes + row0 * 128;
                                 if constexpr (kCluster > 1)
-                                    tma_load_5d_multicast(dst, map, &kv_full[slot], hf * 64, it.hk, slot0, p.layer, page, cmask);
+                                    tma_load_5d_multicast_hint(dst, map, &kv_full[slot], hf * 64, it.hk, slot0, p.layer, page, cmask,
+                                                               kHintKV);
                                 else
-                                    tma_load_5d(dst, map, &kv_full[slot], hf * 64, it.hk, slot0, p.layer, page);
+                                    tma_load_5d_hint(dst, map, &kv_full[slot], hf * 64, it.hk, slot0, p.layer, page, kHintKV);
                             }
                         }
                     } else if constexpr (kCluster > 1) {
@@ -853,20 +928,22 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         // (map_k / map_v carry 64-row boxes in this mode)
 #pragma unroll
                         for (int hf = 0; hf < kHalves; ++hf)
-                            tma_load_4d_multicast(sKV + slot * kTileBytes + hf * kSubTileBytes + rank * (kHN * 128), map,
-                                                  &kv_full[slot], hf * 64, j * kBN + rank * kHN, it.hk, it.b, cmask);
+                            tma_load_4d_multicast_hint(sKV + slot * kTileBytes + hf * kSubTileBytes + rank * (kHN * 128), map,
+                                                       &kv_full[slot], hf * 64, j * kBN + rank * kHN, it.hk, it.b, cmask, kHintKV);
                     } else {
 #pragma unroll
                         for (int hf = 0; hf < kHalves; ++hf)
-                            tma_load_4d(sKV + slot * kTileBytes + hf * kSubTileBytes, map, &kv_full[slot], hf * 64, j * kBN,
-                                        it.hk, it.b);
+                            tma_load_4d_hint(sKV + slot * kTileBytes + hf * kSubTileBytes, map, &kv_full[slot], hf * 64, j * kBN,
+                                             it.hk, it.b, kHintKV);
                     }
                     ++kv_cnt;
                 };
                 int page = page_of(0);
                 int page1 = page_of(it.n_kv > 1 ? 1 : 0);
-                load_q(0);
+                // the first K tile goes out BEFORE the wait for the Q buffers (q_empty fires two half-steps before the
+                // previous item ends; K/V ring slots are usually free earlier), so it is in flight while Q is waited for
                 load_kv(&map_k, 0, page, do_k);
+                load_q(0);
                 load_q(1);
                 load_kv(&map_v, 0, page, do_v);
                 for (int j = 1; j < it.n_kv; ++j) {
@@ -1661,6 +1738,17 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
     int grid = sm_count() > 0 ? sm_count() : 148;
     p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);   // in 128- or 256-row slots
     if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
+    {
+        const int gi = p.head_pairs ? group / 2 : group;                  // items per (KV group, slot)
+        const int per_slot = B * Hkv * gi;
+        p.group = group;
+        p.cnt_last = p.num_pairs % p.pair_block ? p.num_pairs % p.pair_block : p.pair_block;
+        p.fd_block = make_fastdiv((uint32_t)(p.pair_block * per_slot));
+        p.fd_group_full = make_fastdiv((uint32_t)(p.pair_block * gi));
+        p.fd_group_last = make_fastdiv((uint32_t)(p.cnt_last * gi));
+        p.fd_gi = make_fastdiv((uint32_t)gi);
+        p.fd_hkv = make_fastdiv((uint32_t)Hkv);
+    }
 #if PLI_TUNING
     p.trace = g_trace_buf;
     p.trace_cap = g_trace_cap;
@@ -1675,7 +1763,7 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
     p.table_stride = p.page_size = p.page_shift = p.layer = p.box_rows = 0;
     p.cu_q = nullptr;
     p.o_base = nullptr;
-    p.o_st_tok = p.o_st_head = 0;
+    p.o_st_tok = p.o_st_head = p.o_st_batch = 0;
     p.lse_sb = (int64_t)Hq * Nq;
     p.lse_sh = Nq;
 }
@@ -1718,11 +1806,12 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
     p.page_shift = block_size == 16 ? 4 : block_size == 32 ? 5 : block_size == 64 ? 6 : 7;
     p.layer = layer;
     p.box_rows = box_rows;
+    p.o_base = static_cast<uint8_t*>(o);
+    p.o_st_batch = packed ? 0 : os[0];
+    p.o_st_head = os[1];
+    p.o_st_tok = os[2];
     if (packed) {
         p.cu_q = cu_seqlens_q;
-        p.o_base = static_cast<uint8_t*>(o);
-        p.o_st_head = os[1];
-        p.o_st_tok = os[2];
         p.lse_sb = 0;               // lse is (Hq, total_q)
         p.lse_sh = total_q;
     }
@@ -1819,6 +1908,12 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     p.scale_log2 = scale * kLog2e;
     fill_schedule(p, B, Hq, Hkv, Nq);
     if (p.total_items < 0) return set_error(PLI_ERR_UNSUPPORTED, "too many work items");
+    if (peer == nullptr) {                    // raw output address for the register -> global epilogue
+        p.o_base = static_cast<uint8_t*>(o);
+        p.o_st_batch = os[0];
+        p.o_st_head = os[1];
+        p.o_st_tok = os[2];
+    }
     const bool bf16 = dtype == PLI_BF16;
 #define PLI_GO(DD, BF)                                                                            \
     return pairs ? launch_t<DD, BF, 2>(mq, mk, mv, mo, p, stream, pm) : launch_t<DD, BF, 1>(mq, mk, mv, mo, p, stream, pm)

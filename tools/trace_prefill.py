@@ -7,6 +7,10 @@ from physics_llm_inference_b200 import _lib
 
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 B, Hq, Hkv, N, D = 4, 32, 8, 8192, 128
+# argv[3], argv[4]: batch and sequence length (short sequences: "0 20 64 512" prints the FULL timeline of CTA 0's first items)
+if len(sys.argv) > 4:
+    B, N = int(sys.argv[3]), int(sys.argv[4])
+SHORT = N <= 2048
 q = torch.randn(B, Hq, N, D, device="cuda").bfloat16()
 k = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
 v = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
@@ -39,7 +43,13 @@ t0 = recs[0][0]
 span = recs[-1][0] - t0
 print(f"CTA 0: {span} SM cycles between its first and last event = {span / ms / 1e3:.0f} MHz if they span the kernel "
       f"(the SM clock the kernel actually ran at; nvidia-smi's samples are too coarse to see it)")
-names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "S_in_registers", 7: "exp_done", 8: "corr_start", 9: "corr_posted"}
+names = {1: "S_ready", 2: "max_done", 3: "P_posted", 4: "mma_inputs_ready", 5: "mma_issued", 6: "S_in_registers", 7: "exp_done", 8: "corr_start", 9: "corr_posted", 10: "epilogue_start", 11: "epilogue_done", 12: "q_k_landed"}
+if SHORT:
+    print("every event of CTA 0's first ~60k cycles (all items)")
+    for clk, ev, t, j in recs:
+        if clk - t0 < 60000:
+            print(f"  {clk - t0:8d}  tile{t} j={j:3d} {names[ev]}")
+    sys.exit(0)
 print("first item: events of half-steps 40..44 (regions: softmax tile 0/1, MMA warp of tile 0/1)")
 for clk, ev, t, j in recs:
     if 40 <= j <= 44 and clk - t0 < 800000:
