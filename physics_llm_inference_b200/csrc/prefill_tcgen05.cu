@@ -621,9 +621,9 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // go from registers to global memory under a predicate (uniform over the 128 epilogue threads)
                 bool direct = false;
                 if constexpr (kPaged) direct = p.cu_q != nullptr && q_tile0 + kBM > it.nq;
-                // Every tile straight from the registers (no shared-memory staging, no TMA store, no CTA-wide barriers)
-                // when the output is local: the staged path serialises four named barriers and two waits for the
-                // previous TMA store's shared-memory read per tile, which is what short items are made of.
+                // (Sending EVERY tile this way — no staging, no TMA store, no CTA-wide barriers — was measured and is slower:
+                // a warp's 16-byte stores to 32 different rows cost more than the barriers they save; the per-tile epilogue
+                // went from ~2500 to ~3500 cycles and N = 512 from 560 to 500 TFLOP/s.  -DPLI_DIRECT_EPILOGUE=1 rebuilds it.)
                 if (kDirectEpilogue && p.o_base != nullptr && peers.n == 0) direct = true;
 #pragma unroll
                 for (int hf = 0; hf < kHalves; ++hf) {
@@ -848,11 +848,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const WorkItem it = decode_item(w, p);
                 auto load_q = [&](int t) {
                     if (lane == 0 && do_k) {
-#if defined(PLI_PRODUCER_SPIN) && PLI_PRODUCER_SPIN
-                        mbar_wait(&q_empty[t], item_par ^ 1);          // once per item, and the next item starts behind it
-#else
-                        mbar_wait_relaxed(&q_empty[t], item_par ^ 1);
-#endif
+                        mbar_wait_relaxed(&q_empty[t], item_par ^ 1);   // (a spinning wait here measured neutral)
                         if constexpr (kPairMma) {
                             // both CTAs' Q tiles are counted by the leader's barrier (its MMA warp issues for the pair)
                             if (rank == 0) mbar_arrive_expect_tx(&q_full[t], 2 * kTileBytes);
