@@ -13,7 +13,7 @@ include/pli_attention.h).  Importing the package does not need a GPU; calling an
 fails loudly if the library has not been built.
 """
 from ._lib import LIB_PATH, PliError, launch_count, reset_launch_count
-from .decode import (decode_kernel_kind, decode_num_splits, decode_with_cache, decode_with_paged, decode_workspace,
+from .decode import (DecodePlan, decode_kernel_kind, decode_num_splits, decode_with_cache, decode_with_paged, decode_workspace,
                      flash_decode, mixed_batch_attention, paged_gather, prefill_with_paged)
 from .flash_attention import (FlashAttentionConfig, attention_flops, flash_attention, flash_attention_forward,
                               flash_attention_memory_bytes, flash_attention_paged, flash_attention_varlen_paged,
@@ -31,7 +31,7 @@ __all__ = [
     "FlashAttentionConfig", "attention_flops", "attention_memory_bytes", "attention_arithmetic_intensity",
     "AttentionMemoryStats", "online_softmax", "online_softmax_with_output", "standard_softmax",
     "flash_attention_memory_bytes", "prefill_algorithmic_flops", "prefill_kernel_kind",
-    "flash_decode", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
+    "flash_decode", "DecodePlan", "decode_with_cache", "decode_with_paged", "decode_num_splits", "decode_workspace",
     "decode_kernel_kind", "paged_gather", "prefill_with_paged", "mixed_batch_attention",
     "KVCache", "LayerKVCache", "create_caches", "kv_append", "BlockTable", "PagedKVCache",
     "GroupedQueryAttention", "CachedGQA", "DecodeGraphRunner", "TensorParallelGQA",

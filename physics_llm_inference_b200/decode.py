@@ -28,7 +28,7 @@ def decode_workspace(B: int, Hq: int, D: int, num_splits: int, device) -> torch.
     return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
 
 
-def flash_decode(
+def _prepare_decode(
     q: torch.Tensor,
     k_cache: torch.Tensor,
     v_cache: torch.Tensor,
@@ -142,59 +142,92 @@ def flash_decode(
         workspace = torch.empty(need // 4, dtype=torch.float32, device=dev)
     elif workspace.numel() * workspace.element_size() < need or not workspace.is_cuda:
         raise RuntimeError(f"workspace too small: need {need} bytes")
+    lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
+    lse_ptr = lse.data_ptr() if lse is not None else None
+    ws_bytes = workspace.numel() * workspace.element_size()
+    keep = (q3, k_cache, v_cache, block_tables, lens, workspace, lse)       # the launch only holds raw pointers
     if peer_out is not None:
-        return _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer,
-                               kv_extent, kv_strides, scale, num_splits, workspace, peer_out, return_lse)
+        import ctypes
+        sh = peer_out.shard
+        Bt, Ht, Dt = peer_out.shape
+        if (B, Hq, D) != (sh.b_end - sh.b_start, sh.q_end - sh.q_start, Dt) or peer_out.dtype != q3.dtype:
+            raise RuntimeError(f"local decode shape {(B, Hq, D)} / dtype does not match the PeerOutput shard")
+        ps = _lib.PeerScatter()
+        ps.n_peers, ps.rank = sh.world_size, sh.rank
+        for r in range(sh.world_size):
+            ps.peer_o[r] = peer_out.output_ptrs[r]
+            ps.peer_flags[r] = peer_out.flag_ptrs[r]
+        ps.epoch = peer_out.epoch_ptr
+        ps.buffer_stride = peer_out.buffer_stride
+        ps.slice_offset = peer_out.slice_offset
+        ps_ref = ctypes.byref(ps)
+        args = (q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(), lse_ptr, B, Hq, Hkv, D,
+                max_seq_len, bs, tstride, layer, kv_extent, _lib.i64(q3.stride(0), q3.stride(1)), _lib.i64(*kv_strides),
+                _lib.i64(Ht * Dt, Dt), float(scale), _lib.dtype_code(q3.dtype), num_splits, workspace.data_ptr(), ws_bytes,
+                ps_ref)
+        return _Prepared(dev, True, args, keep + (ps,), None, lse, peer_out, ps, q.dim() == 4)
     if out is None:
         out = torch.empty((B, Hq, D), dtype=q.dtype, device=dev)
     elif out.shape != (B, Hq, D) or out.dtype != q.dtype or out.stride(-1) != 1:
         raise RuntimeError("out must be (B, Hq, D), q's dtype, unit inner stride")
-    lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
-
-    with _lib.on_device(dev):
-        rc = lib.pli_decode_fwd(
-            q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(), out.data_ptr(),
-            lse.data_ptr() if lse is not None else None, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
-            _lib.i64(q3.stride(0), q3.stride(1)), _lib.i64(*kv_strides), _lib.i64(out.stride(0), out.stride(1)),
-            float(scale), _lib.dtype_code(q.dtype), num_splits, workspace.data_ptr(),
-            workspace.numel() * workspace.element_size(), _lib.current_stream_ptr(dev))
-    _lib.check(rc)
-    o = out.unsqueeze(2) if q.dim() == 4 else out
-    return (o, lse) if return_lse else o
+    args = (q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(), out.data_ptr(), lse_ptr,
+            B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent, _lib.i64(q3.stride(0), q3.stride(1)),
+            _lib.i64(*kv_strides), _lib.i64(out.stride(0), out.stride(1)), float(scale), _lib.dtype_code(q.dtype),
+            num_splits, workspace.data_ptr(), ws_bytes)
+    return _Prepared(dev, False, args, keep, out, lse, None, None, q.dim() == 4)
 
 
-def _decode_scatter(q3, k_cache, v_cache, table_ptr, lens, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
-                    kv_strides, scale, num_splits, workspace, peer_out, return_lse):
-    sh = peer_out.shard
-    Bt, Ht, Dt = peer_out.shape
-    if (B, Hq, D) != (sh.b_end - sh.b_start, sh.q_end - sh.q_start, Dt) or peer_out.dtype != q3.dtype:
-        raise RuntimeError(f"local decode shape {(B, Hq, D)} / dtype does not match the PeerOutput shard")
-    dev = q3.device
-    lse = torch.empty((B, Hq), dtype=torch.float32, device=dev) if return_lse else None
-    ps = _lib.PeerScatter()
-    ps.n_peers, ps.rank = sh.world_size, sh.rank
-    for r in range(sh.world_size):
-        ps.peer_o[r] = peer_out.output_ptrs[r]
-        ps.peer_flags[r] = peer_out.flag_ptrs[r]
-    ps.epoch = peer_out.epoch_ptr
-    ps.buffer_stride = peer_out.buffer_stride
-    ps.slice_offset = peer_out.slice_offset
-    lib = _lib.load()
-    import ctypes
-    with _lib.on_device(dev):
-        stream = _lib.current_stream_ptr(dev)
-        rc = lib.pli_decode_fwd_scatter(
-            q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(),
-            lse.data_ptr() if lse is not None else None, B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent,
-            _lib.i64(q3.stride(0), q3.stride(1)), _lib.i64(*kv_strides), _lib.i64(Ht * Dt, Dt), float(scale),
-            _lib.dtype_code(q3.dtype), num_splits, workspace.data_ptr(), workspace.numel() * workspace.element_size(),
-            ctypes.byref(ps), stream)
-        _lib.check(rc)
-        _lib.check(lib.pli_peer_publish_wait(ctypes.byref(ps), stream))
-        # eager: the buffer of this step; under stream capture (nothing ran yet): the fixed `stable` tensor the captured
-        # step copies into — the caller accounts for replays with peer_out.advance(n)
-        o = peer_out.finish_step(ps, stream)
-    return (o, lse) if return_lse else o
+class _Prepared:
+    """A validated, marshalled decode call: everything but the stream."""
+    __slots__ = ("dev", "scatter", "args", "keep", "out", "lse", "peer_out", "ps", "four_d", "lib")
+
+    def __init__(self, dev, scatter, args, keep, out, lse, peer_out, ps, four_d):
+        self.dev, self.scatter, self.args, self.keep = dev, scatter, args, keep
+        self.out, self.lse, self.peer_out, self.ps, self.four_d = out, lse, peer_out, ps, four_d
+        self.lib = _lib.load()
+
+    def launch(self):
+        with _lib.on_device(self.dev):
+            stream = _lib.current_stream_ptr(self.dev)
+            if self.scatter:
+                import ctypes
+                _lib.check(self.lib.pli_decode_fwd_scatter(*self.args, stream))
+                _lib.check(self.lib.pli_peer_publish_wait(ctypes.byref(self.ps), stream))
+                # eager: the buffer of this step; under stream capture (nothing ran yet): the fixed `stable` tensor the
+                # captured step copies into — the caller accounts for replays with peer_out.advance(n)
+                o = self.peer_out.finish_step(self.ps, stream)
+            else:
+                _lib.check(self.lib.pli_decode_fwd(*self.args, stream))
+                o = self.out.unsqueeze(2) if self.four_d else self.out
+        return (o, self.lse) if self.lse is not None else o
+
+
+def flash_decode(q, k_cache, v_cache, seq_lens, *, block_tables=None, layer: int = 0, scale: float | None = None,
+                 return_lse: bool = False, num_splits: int | None = None, max_seq_len: int | None = None,
+                 workspace: torch.Tensor | None = None, out: torch.Tensor | None = None, peer_out=None,
+                 validate: bool = False):
+    return _prepare_decode(q, k_cache, v_cache, seq_lens, block_tables=block_tables, layer=layer, scale=scale,
+                           return_lse=return_lse, num_splits=num_splits, max_seq_len=max_seq_len, workspace=workspace,
+                           out=out, peer_out=peer_out, validate=validate).launch()
+
+
+flash_decode.__doc__ = _prepare_decode.__doc__
+
+
+class DecodePlan:
+    """`flash_decode` with the validation and argument marshalling done ONCE: `plan = DecodePlan(q, k_cache, v_cache,
+    seq_lens, block_tables=..., out=..., ...)`, then `plan()` per step launches on the current stream with the same
+    buffers (new queries / lengths are written into them in place, as a CUDA-graph runner does).  A decode step of a few
+    tens of microseconds is otherwise bound by the ~30 us the Python wrapper spends per call; a plan call costs a few.
+    Same arguments and results as `flash_decode`."""
+
+    def __init__(self, q, k_cache, v_cache, seq_lens, **kw):
+        if isinstance(seq_lens, int):
+            raise TypeError("a plan needs seq_lens as a (B,) CUDA int32 tensor (it is read on the device at every step)")
+        self._prep = _prepare_decode(q, k_cache, v_cache, seq_lens, **kw)
+
+    def __call__(self):
+        return self._prep.launch()
 
 
 def decode_kernel_kind(k_cache: torch.Tensor, block_tables=None) -> str:

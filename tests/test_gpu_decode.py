@@ -276,3 +276,39 @@ def test_decode_peer_output_single_rank(splits):
         assert o.shape == (B, Hq, D)
         assert torch.equal(o, ref), step
     assert po.epoch == 3
+
+
+def test_decode_plan_matches_flash_decode_and_replays_in_a_graph():
+    """`DecodePlan`: the call marshalled once, launched many times; same bits as `flash_decode`, follows in-place updates
+    of its buffers, and captures into a CUDA graph."""
+    B, Hq, Hkv, D, bs = 5, 8, 2, 128, 16
+    lens_l = [300, 17, 1024, 64, 999]
+    q, kp, vp, table, lens = orc.seeded_paged(77, B, Hq, Hkv, D, bs, lens_l, dtype=torch.bfloat16)
+    qd, kd, vd, td, ld = q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens.cuda()
+    ref, rl = pli.flash_decode(qd, kd, vd, ld, block_tables=td, max_seq_len=1024, return_lse=True)
+    out = torch.empty(B, Hq, D, device="cuda", dtype=torch.bfloat16)
+    plan = pli.DecodePlan(qd, kd, vd, ld, block_tables=td, max_seq_len=1024, out=out, return_lse=True)
+    o, l = plan()
+    assert o.data_ptr() == out.data_ptr() and torch.equal(o, ref) and torch.equal(l, rl)
+    # in-place update of the planned buffers: shorter sequences, another query
+    ld.copy_(torch.tensor([100, 17, 500, 1, 640], dtype=torch.int32))
+    qd.mul_(-0.5)
+    ref2 = pli.flash_decode(qd, kd, vd, ld, block_tables=td, max_seq_len=1024)
+    o2, _ = plan()
+    assert torch.equal(o2, ref2) and not torch.equal(ref2, ref)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            plan()
+    torch.cuda.current_stream().wait_stream(side)
+    qd.add_(0.25)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out.unsqueeze(2), pli.flash_decode(qd, kd, vd, ld, block_tables=td, max_seq_len=1024))
+    with pytest.raises(TypeError):
+        pli.DecodePlan(qd, kd, vd, 300, block_tables=td)
