@@ -496,6 +496,22 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* r) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+// n consecutive 32-bit columns (n a multiple of 4 / 8) as the largest power-of-two pieces
+template <int kCols>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r);
+template <int kCols>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* r);
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
                  "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -528,6 +544,22 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* r) {
         "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
         "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
+}
+
+template <int kCols>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* r) {
+    static_assert(kCols % 4 == 0 && kCols <= 32, "P columns: a multiple of 4, at most 32");
+    if constexpr (kCols >= 32) { tmem_st_x32(taddr, r); }
+    else if constexpr (kCols >= 16) { tmem_st_x16(taddr, r); tmem_st_cols<kCols - 16>(taddr + 16, r + 16); }
+    else if constexpr (kCols >= 8) { tmem_st_x8(taddr, r); tmem_st_cols<kCols - 8>(taddr + 8, r + 8); }
+    else if constexpr (kCols >= 4) { tmem_st_x4(taddr, r); }
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* r) {
+    static_assert(kCols % 8 == 0 && kCols <= 64, "S columns: a multiple of 8, at most 64");
+    if constexpr (kCols >= 32) { tmem_ld_x32(taddr, r); tmem_ld_cols<kCols - 32>(taddr + 32, r + 32); }
+    else if constexpr (kCols >= 16) { tmem_ld_x16(taddr, r); tmem_ld_cols<kCols - 16>(taddr + 16, r + 16); }
+    else if constexpr (kCols >= 8) { tmem_ld_x8(taddr, r); }
 }
 
 // ---- UMMA descriptors ------------------------------------------------------------------------

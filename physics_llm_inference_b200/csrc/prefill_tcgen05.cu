@@ -53,6 +53,14 @@ constexpr int kCorrCols = PLI_CORR_COLS;
 #ifndef PLI_L2_HINTS
 #define PLI_L2_HINTS 1
 #endif
+// Option (off): software-pipelined softmax (pipelined_step in the kernel; needs the 48 / 16 column split): the thread
+// loads S(s+1) and folds it into the next row maximum between the exponentials of S(s).  Correct (all parity tests),
+// 14 % SLOWER on C2 (1146-1158 against 1332 TFLOP/s, profiles/r02_ab_softmax_pipeline.log): S(s+1) overwrites P(s-1), so it
+// is issued behind PV(s-1) and completes ~800-1400 cycles after P(s-1) was posted -- i.e. near the END of step s; a wait
+// for it inside step s stalls the exponentials.
+#ifndef PLI_SOFTMAX_PIPELINE
+#define PLI_SOFTMAX_PIPELINE 0
+#endif
 #ifndef PLI_DIRECT_EPILOGUE
 #define PLI_DIRECT_EPILOGUE 0
 #endif
@@ -60,7 +68,15 @@ constexpr bool kDirectEpilogue = PLI_DIRECT_EPILOGUE != 0;
 constexpr uint64_t kHintQ = PLI_L2_HINTS ? kL2EvictFirst : 0x1000000000000000ull;    // else: evict-normal
 constexpr uint64_t kHintKV = PLI_L2_HINTS ? kL2EvictLast : 0x1000000000000000ull;
 constexpr uint64_t kHintO = PLI_L2_HINTS ? kL2EvictFirst : 0x1000000000000000ull;
-static_assert(kCorrCols == 0 || kCorrCols == 16 || kCorrCols == 32, "kCorrCols: 0, 16 or 32 of the 64 columns");
+static_assert(kCorrCols >= 0 && kCorrCols <= 32 && kCorrCols % 8 == 0, "kCorrCols: 0, 8, 16, 24 or 32 of the 64 columns");
+// Option (off): the correction warp loads its share of S(s) as soon as S(s) is complete (its own wait on s_full), i.e.
+// BEFORE the softmax warp has posted the row maximum, to hide the ~200-cycle tensor-memory load behind that wait.
+// Measured 4 % SLOWER on C2 (1245-1253 against 1293-1295 TFLOP/s, profiles/r02_ab_corr_prefetch.log): the extra barrier
+// poll and the earlier TMEM traffic cost more than the latency they hide.
+#ifndef PLI_CORR_PREFETCH
+#define PLI_CORR_PREFETCH 0
+#endif
+constexpr bool kCorrPrefetch = PLI_CORR_PREFETCH != 0;
 #ifndef PLI_PROFILE
 #define PLI_PROFILE 0                     // 1: compile the in-kernel timeline / phase counters (tuning builds only)
 #endif
@@ -191,16 +207,15 @@ __device__ __noinline__ void rescale_o_rows(uint32_t o_addr, float alpha) {
     }
 }
 
-// P = exp2(S * c - m * c) for 16 scores of a row: packed FFMA2 for the argument, MUFU.EX2 (an FMA-pipe polynomial for
-// kPolyPairs of every 16 pairs), row sums in two packed FADD2 chains, bf16/f16 pairs packed into pk[0..8).
-template <bool kBf16>
-__device__ __forceinline__ void exp_chunk16(const float* sv, float2 c2, float2 nmc2, float2& acc0, float2& acc1,
-                                            uint32_t* pk) {
+// P = exp2(S * c - m * c) for kCols scores of a row: packed FFMA2 for the argument, MUFU.EX2 (an FMA-pipe polynomial for
+// kPolyPairs of every 16 pairs), row sums in two packed FADD2 chains, bf16/f16 pairs packed into pk[0, kCols / 2).
+template <bool kBf16, int kCols>
+__device__ __forceinline__ void exp_cols(const float* sv, float2 c2, float2 nmc2, float2& acc0, float2& acc1, uint32_t* pk) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < kCols / 2; ++i) {
         const float2 x = ffma2(make_float2(sv[2 * i], sv[2 * i + 1]), c2, nmc2);
         float2 pv;
-        if (i < kPolyPairs / 2) {
+        if ((i & 7) < kPolyPairs / 2) {
             pv = exp2_poly2(x);
         } else {
             pv.x = ex2_approx(x.x);
@@ -476,22 +491,23 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 const float2 c2 = make_float2(c, c);
                 const float2 nmc2 = make_float2(nmc, nmc);
                 float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-                const int n_chunks = (kInterior || s > 0) ? (kHN - kCorrCols) / 16 : 4;   // warp-uniform
+                constexpr int kSoft = kHN - kCorrCols;                // this warp's columns of a step s >= 1
                 {
                     uint32_t pk[16];
-                    exp_chunk16<kBf16>(sv + 0, c2, nmc2, acc0, acc1, pk);
-                    exp_chunk16<kBf16>(sv + 16, c2, nmc2, acc0, acc1, pk + 8);
+                    exp_cols<kBf16, 32>(sv, c2, nmc2, acc0, acc1, pk);
                     tmem_st_x16(s_addr, pk);
                 }
-                if (kCorrCols < 32 || (!kInterior && n_chunks > 2)) {
-                    uint32_t pk[8];
-                    exp_chunk16<kBf16>(sv + 32, c2, nmc2, acc0, acc1, pk);
-                    tmem_st_x8(s_addr + 16, pk);
+                if constexpr (kSoft > 32) {
+                    uint32_t pk[(kSoft - 32) / 2];
+                    exp_cols<kBf16, kSoft - 32>(sv + 32, c2, nmc2, acc0, acc1, pk);
+                    tmem_st_cols<(kSoft - 32) / 2>(s_addr + 16, pk);
                 }
-                if (kCorrCols < 16 || (!kInterior && n_chunks > 3)) {
-                    uint32_t pk[8];
-                    exp_chunk16<kBf16>(sv + 48, c2, nmc2, acc0, acc1, pk);
-                    tmem_st_x8(s_addr + 24, pk);
+                if constexpr (!kInterior && kCorrCols > 0) {
+                    if (s == 0) {                                     // step 0: the whole row (warp-uniform)
+                        uint32_t pk[kCorrCols / 2];
+                        exp_cols<kBf16, kCorrCols>(sv + kSoft, c2, nmc2, acc0, acc1, pk);
+                        tmem_st_cols<kCorrCols / 2>(s_addr + kSoft / 2, pk);
+                    }
                 }
                 acc0 = fadd2(acc0, acc1);
                 d += acc0.x + acc0.y;
@@ -505,10 +521,114 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             // half-steps [1, n_plain) are interior: 64 (s + 1) <= nk and, when causal, 64 s + 63 <= q_tile0 + off
             int n_plain = min(nt, nk / kHN);
             if (p.causal) n_plain = min(n_plain, q_tile0 + off - (kHN - 1) >= 0 ? (q_tile0 + off - (kHN - 1)) / kHN + 1 : 0);
+#if PLI_SOFTMAX_PIPELINE
+            // ---- interior half-steps, software-pipelined across steps ----
+            // While the exponentials of S(s) run (MUFU / issue bound), the thread loads S(s+1) 16 columns at a time and
+            // folds them into the next row maximum, so the ~230-cycle tensor-memory load and the ~500-cycle maximum of
+            // step s+1 hide inside step s instead of heading its chain (S runs two half-steps ahead, so S(s+1) is
+            // normally complete).  cur holds S(s) with its row maximum known; nxt receives S(s+1).  Two copies of the
+            // step with the arrays swapped, so nothing is moved between steps.
+            auto max16 = [](const float* v, float m) -> float {
+                float a = fmaxf(v[0], v[1]), b = fmaxf(v[2], v[3]);
+#pragma unroll
+                for (int i = 4; i < 16; i += 4) {
+                    a = fmaxf(a, fmaxf(v[i], v[i + 1]));
+                    b = fmaxf(b, fmaxf(v[i + 2], v[i + 3]));
+                }
+                return fmaxf(m, fmaxf(a, b));
+            };
+            auto pipelined_step = [&](const int s, float (&cur)[64], float (&nxt)[64], const float mx_cur, float& mx_next,
+                                      const bool has_next) {
+                constexpr int kSoft = kHN - kCorrCols;
+                static_assert(kSoft == 48, "the pipelined step is written for the 48 / 16 column split");
+                const int h = s & 1;
+                const uint32_t s_addr = tmem_base + t * 128 + h * 64 + lane_addr;
+                const uint32_t n_addr = tmem_base + t * 128 + (h ^ 1) * 64 + lane_addr;
+                const float m_new = fmaxf(mx_cur, m_ref);
+                float alpha = 1.f;
+                if ((m_new - m_ref) * c > kRescaleThreshold) {
+                    alpha = ex2_approx((m_ref - m_new) * c);
+                    m_ref = m_new;
+                    d *= alpha;
+                }
+                const float nmc = m_ref == -INFINITY ? 0.f : -m_ref * c;
+                sScale[(t * 2 + h) * 128 + row] = alpha;
+                sNmc[(t * 2 + h) * 128 + row] = nmc;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sc_full[t * 2 + h]);
+                if (has_next) {
+                    mbar_wait(&s_full[t * 2 + (h ^ 1)], (sf_par >> (h ^ 1)) & 1);
+                    sf_par ^= 1u << (h ^ 1);
+                    tc_fence_after();
+                    tmem_ld_x16(n_addr + 48, nxt + 48);               // the correction warp's columns: needed for the maximum only
+                }
+                const float2 c2 = make_float2(c, c);
+                const float2 nmc2 = make_float2(nmc, nmc);
+                float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+                float mx = -INFINITY;
+                uint32_t pk[16];
+                exp_cols<kBf16, 16>(cur, c2, nmc2, acc0, acc1, pk);
+                if (has_next) {
+                    tc_wait_ld();
+                    mx = max16(nxt + 48, mx);
+                    tmem_ld_x16(n_addr, nxt);
+                }
+                exp_cols<kBf16, 16>(cur + 16, c2, nmc2, acc0, acc1, pk + 8);
+                tmem_st_x16(s_addr, pk);
+                if (has_next) {
+                    tc_wait_ld();
+                    mx = max16(nxt, mx);
+                    tmem_ld_x16(n_addr + 16, nxt + 16);
+                }
+                exp_cols<kBf16, 16>(cur + 32, c2, nmc2, acc0, acc1, pk);
+                tmem_st_x8(s_addr + 16, pk);
+                if (has_next) {
+                    tc_wait_ld();
+                    mx = max16(nxt + 16, mx);
+                    tmem_ld_x16(n_addr + 32, nxt + 32);
+                }
+                acc0 = fadd2(acc0, acc1);
+                d += acc0.x + acc0.y;
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_pv_ok(t * 2 + h);
+                if (has_next) {
+                    tc_wait_ld();
+                    mx = max16(nxt + 32, mx);
+                }
+                mx_next = mx;
+            };
+            half_step(0, std::false_type{});
+            int s = 1;
+            if (s < n_plain) {
+                float sa[64], sb[64];
+                float mxa = -INFINITY, mxb = -INFINITY;
+                {
+                    const uint32_t a_addr = tmem_base + t * 128 + 64 + lane_addr;      // step 1: buffer 1
+                    mbar_wait(&s_full[t * 2 + 1], (sf_par >> 1) & 1);
+                    sf_par ^= 2u;
+                    tc_fence_after();
+                    tmem_ld_x32(a_addr, sa);
+                    tmem_ld_x32(a_addr + 32, sa + 32);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 64; i += 16) mxa = max16(sa + i, mxa);
+                }
+                for (;;) {
+                    pipelined_step(s, sa, sb, mxa, mxb, s + 1 < n_plain);
+                    if (++s >= n_plain) break;
+                    pipelined_step(s, sb, sa, mxb, mxa, s + 1 < n_plain);
+                    if (++s >= n_plain) break;
+                }
+            }
+            for (; s < nt; ++s) half_step(s, std::false_type{});
+#else
             for (int s = 0; s < nt; ++s) {
                 if (s >= 1 && s < n_plain) half_step(s, std::true_type{});
                 else half_step(s, std::false_type{});
             }
+#endif
             mbar_wait(&stats_free[t], item_par ^ 1);      // previous item's epilogue has read the slots
             sSum[t * 128 + row] = d;
             sMax[t * 128 + row] = m_ref * c;              // log2 units
@@ -541,6 +661,15 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 for (int t = 0; t < 2; ++t) {
                     if (s >= it.n[t]) continue;
                     const int bi = t * 2 + h;
+                    [[maybe_unused]] float sv[kCorrCols > 0 ? kCorrCols : 1];
+                    [[maybe_unused]] const uint32_t s_addr = tmem_base + t * 128 + h * 64 + lane_addr;
+                    if constexpr (kCorrCols > 0 && kCorrPrefetch) {
+                        // S_t(s) complete?  (This phase of s_full cannot be overtaken: S_t(s+2) is only issued behind
+                        // PV_t(s), which needs this warp's arrival for step s.)  Then fetch the share now.
+                        mbar_wait(&s_full[bi], ((sf_base >> bi) ^ (uint32_t)(s >> 1)) & 1u);
+                        tc_fence_after();
+                        tmem_ld_cols<kCorrCols>(s_addr + (kHN - kCorrCols), sv);
+                    }
 #if defined(PLI_CORR_SPIN) && PLI_CORR_SPIN
                     mbar_wait(&sc_full[bi], (sc_par >> bi) & 1);
 #else
@@ -554,12 +683,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         // read the whole row and posted -m_ref * c next to the scale factor)
                         const float nmc = sNmc[bi * 128 + row];
                         const float cs = p.scale_log2;
-                        const uint32_t s_addr = tmem_base + t * 128 + h * 64 + lane_addr;
-                        tc_fence_after();
-                        float sv[kCorrCols];
-#pragma unroll
-                        for (int cc = 0; cc < kCorrCols / 16; ++cc)
-                            tmem_ld_x16(s_addr + (kHN - kCorrCols) + cc * 16, sv + cc * 16);
+                        if constexpr (!kCorrPrefetch) {
+                            tc_fence_after();
+                            tmem_ld_cols<kCorrCols>(s_addr + (kHN - kCorrCols), sv);
+                        }
                         tc_wait_ld();
                         const int k0 = s * kHN, off = it.nk - it.nq;
                         const bool need_mask = (k0 + kHN > it.nk) || (p.causal && (k0 + kHN - 1 > it.q0[t] + off));
@@ -572,11 +699,10 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         }
                         const float2 c2 = make_float2(cs, cs), nmc2 = make_float2(nmc, nmc);
                         float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
-#pragma unroll
-                        for (int cc = 0; cc < kCorrCols / 16; ++cc) {
-                            uint32_t pk[8];
-                            exp_chunk16<kBf16>(sv + cc * 16, c2, nmc2, acc0, acc1, pk);
-                            tmem_st_x8(s_addr + (kHN - kCorrCols) / 2 + cc * 8, pk);
+                        {
+                            uint32_t pk[kCorrCols / 2];
+                            exp_cols<kBf16, kCorrCols>(sv, c2, nmc2, acc0, acc1, pk);
+                            tmem_st_cols<kCorrCols / 2>(s_addr + (kHN - kCorrCols) / 2, pk);
                         }
                         acc0 = fadd2(acc0, acc1);
                         d_corr[t] = d_corr[t] * alpha + (acc0.x + acc0.y);
