@@ -76,6 +76,7 @@ _SIGNATURES = {
     # debug aid, not declared in the public header
     "pli_debug_umma_selftest": (C.c_int, [_VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, _VP]),
     "pli_debug_prefill_trace": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "pli_debug_decode_trace": (C.c_int, [_VP, C.c_int]),
 }
 
 _lib = None

@@ -212,6 +212,30 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 }
 
 // ---- TMA -------------------------------------------------------------------------------------
+// Division by a launch constant as multiply-high + shift (n < 2^31); the multiplier is found on the host.
+struct FastDiv {
+    uint32_t d, mul, sh;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> sh); }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{d ? d : 1u, 0u, 0u};
+    if (f.d > 1) {
+        uint32_t l = 0;
+        while ((1ull << l) < f.d) ++l;
+        const uint32_t pw = 31 + l;
+        f.mul = (uint32_t)(((1ull << pw) + f.d - 1) / f.d);
+        f.sh = pw - 32;
+    }
+    return f;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
+}
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }

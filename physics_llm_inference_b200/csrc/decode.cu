@@ -12,6 +12,7 @@
 //                       with TMA (one box per page, page ids from the block table), four consumer
 //                       warps run QK^T and PV on mma.sync m16n8k16 via ldmatrix, fp32 softmax state.
 //   decode_simt_kernel  everything else (f32 storage, odd head_dim / page size): CUDA cores.
+#include <atomic>
 #include <cstdlib>
 #include <type_traits>
 
@@ -23,6 +24,13 @@ namespace {
 // Tokens [t0, t1) of sequence length L handled by split s of S (multiples of 64; may be empty).
 __host__ __device__ __forceinline__ void split_range(int L, int S, int s, int& t0, int& t1) {
     int chunk = (((L + S - 1) / S) + 63) & ~63;
+    t0 = min(L, s * chunk);
+    t1 = min(L, t0 + chunk);
+}
+
+// the same with the division by S done as multiply-high + shift (S is a launch constant)
+__device__ __forceinline__ void split_range_fast(int L, int S, const FastDiv& fd, int s, int& t0, int& t1) {
+    const int chunk = ((int)fd.div((uint32_t)(L + S - 1)) + 63) & ~63;
     t0 = min(L, s * chunk);
     t1 = min(L, t0 + chunk);
 }
@@ -117,7 +125,9 @@ __global__ void __launch_bounds__(128) decode_simt_kernel(
 constexpr int kStageTokens = 64;   // tokens per pipeline stage (16 per consumer warp)
 constexpr int kDecodeStages = 3;   // smem ring depth (3 x 32 KB at D=128 -> 2 CTAs per SM)
 constexpr int kConsumerWarps = 4;
-constexpr int kDecodeThreads = (kConsumerWarps + 1) * 32;
+constexpr int kProducerWarps = 2;  // warp 4 loads the K tiles, warp 5 the V tiles: issuing a TMA from lanes with different
+                                   // operands costs ~70 cycles each (an elect / R2UR loop), 16 of them per 16-token-page stage
+constexpr int kDecodeThreads = (kConsumerWarps + kProducerWarps) * 32;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
@@ -182,7 +192,24 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     return v;
 }
 
+#if defined(PLI_TUNING) && PLI_TUNING
+#define PLI_DECODE_TRACE(slot)                                                                                       \
+    do {                                                                                                             \
+        if (p.trace != nullptr) {                                                                                    \
+            const int cta_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;                         \
+            if (cta_ < p.trace_cap) {                                                                                \
+                if ((slot) == 0) p.trace[cta_ * 16 + 7] = global_timer_ns();                                         \
+                p.trace[cta_ * 16 + (slot)] = (unsigned long long)clock64();                                         \
+            }                                                                                                        \
+        }                                                                                                            \
+    } while (0)
+#else
+#define PLI_DECODE_TRACE(slot) do { } while (0)
+#endif
+
 struct DecodeTmaParams {
+    unsigned long long* trace;   // tuning builds: 16 timestamps per CTA (pli_debug_decode_trace), else NULL
+    int trace_cap;
     const void* q;
     const int32_t* table;
     const int32_t* seq_lens;
@@ -192,15 +219,163 @@ struct DecodeTmaParams {
     float* lse_direct;
     int64_t osb, osh;
     int64_t qsb, qsh;
-    int Hq, Hkv, G, bs, table_stride, layer, S, box_tokens;
+    int Hq, Hkv, G, bs, table_stride, layer, S, box_tokens, max_len;
+    int bs_shift, box_shift;          // log2 of bs / box_tokens (both powers of two on this path)
+    FastDiv fd_splits;                // division by S
     float scale_log2;
-    PeerScatter peer;     // peer.n > 0 (direct output only): o_direct is unused, the slice goes to every rank
+    PeerScatter peer;     // peer.n > 0: the final output (direct or combined in this kernel) goes to every rank
+    // S > 1, fused combine: the CTA that arrives LAST on its unit's counter merges the unit's S partials and writes the
+    // final output, so no second kernel follows.  counters == NULL: partials only (pli_decode_splitkv).
+    unsigned long long* counters;   // two 64-bit words per (b, kv head, 16-row chunk), see unit_arrive
+    uint32_t launch_id;
+    void* o_final;                  // with osb / osh; unused when peer.n > 0
+    float* lse_final;               // or NULL
 };
+
+// Arrival of one split's CTA on its unit's counter pair; returns the number of arrivals before this one.
+//   c[0] = kCtrTag | arrivals   the fast path: ONE fetch-add per CTA.  The last arriver stores kCtrTag back (zero arrivals),
+//                               so the next launch -- or the next replay of a CUDA graph -- starts from zero.
+//   c[1] = launch id << 32 | arrivals   only while c[0] does not carry the tag, i.e. the first launch on a workspace that
+//                               was never used (the caller's workspace needs NO initialisation): a compare-and-swap loop
+//                               that treats a word left by anything but this launch as zero.  37 CTAs contending on one
+//                               CAS cost ~25 us, which is why this is not the steady-state protocol.
+// Both atomics are acq_rel at device scope: they release this CTA's partials (ordered before them by the CTA barrier) and
+// acquire those of the splits that arrived earlier.
+constexpr unsigned long long kCtrTag = 0xA5C3D2E1F0ull << 24;       // upper 40 bits; arrivals in the lower 24
+__device__ __forceinline__ uint32_t unit_arrive(unsigned long long* c, uint32_t id, bool& tagged) {
+    unsigned long long old;
+    asm volatile("atom.acq_rel.gpu.global.add.u64 %0, [%1], 1;\n" : "=l"(old) : "l"(c) : "memory");
+    tagged = (old >> 24) == (kCtrTag >> 24);
+    if (tagged) return (uint32_t)(old & 0xFFFFFFull);
+    unsigned long long seen, assumed;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(seen) : "l"(c + 1) : "memory");
+    uint32_t cnt;
+    do {
+        assumed = seen;
+        cnt = (uint32_t)(assumed >> 32) == id ? (uint32_t)assumed : 0u;
+        asm volatile("atom.acq_rel.gpu.global.cas.b64 %0, [%1], %2, %3;\n"
+                     : "=l"(seen)
+                     : "l"(c + 1), "l"(assumed), "l"(((unsigned long long)id << 32) | (cnt + 1u))
+                     : "memory");
+    } while (seen != assumed);
+    return cnt;
+}
+// The last arriver, after the merge: zero arrivals for the next launch (nobody else touches the pair any more).
+__device__ __forceinline__ void unit_reset(unsigned long long* c, uint32_t id, bool tagged) {
+    if (!tagged) c[1] = (unsigned long long)id << 32;
+    c[0] = kCtrTag;
+}
+
+// Merge of the S partials of one unit (rows_here q heads of one sequence) by the 128 consumer threads of the CTA that
+// arrived last: weights from the partial LSEs per row (one warp per row), then (row, split) pairs spread over the threads
+// as float4 loads with two rows' worth in flight, summed across the split slots through shared memory.
+template <int kD, typename elem_t>
+__device__ __forceinline__ void combine_unit(const DecodeTmaParams& p, float* smem_f, int b, int h_base, int rows_here,
+                                             int tid) {
+    const int S = p.S;
+    float* sw = smem_f;                   // [16 rows][64 splits] normalised weights
+    float* red = smem_f + 16 * 64;        // [slots][16 rows][kD]
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kLanesPerRow = kD / 4;                          // float4 per thread
+    constexpr int kSlots = kConsumerWarps * 32 / kLanesPerRow;    // 4 (D 128) or 8 (D 64) split slots
+    constexpr int kDepth = 8;                                     // loads in flight per row
+    const int slot = tid / kLanesPerRow, dv = (tid % kLanesPerRow) * 4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load4 = [&](int row, int sp) -> float4 {
+        return __ldcg(reinterpret_cast<const float4*>(p.o_part + (((int64_t)b * p.Hq + h_base + row) * S + sp) * kD + dv));
+    };
+    auto load_batch = [&](int row, int s0, float4 (&v0)[kDepth], float4 (&v1)[kDepth]) {
+        const bool two = row + 1 < rows_here;
+#pragma unroll
+        for (int j = 0; j < kDepth; ++j) {
+            const int sp = s0 + j * kSlots;
+            v0[j] = sp < S ? load4(row, sp) : zero4;
+            v1[j] = (two && sp < S) ? load4(row + 1, sp) : zero4;
+        }
+    };
+    // the latency chain of the CTA that finishes last is what this costs, so: the partial LSEs AND the first batch of
+    // partial outputs are requested together, the weights are worked out while the outputs are in flight
+    float l0[4], l1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = warp + i * kConsumerWarps;
+        const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * S;
+        l0[i] = (row < rows_here && lane < S) ? __ldcg(p.lse_part + prow + lane) : -INFINITY;
+        l1[i] = (row < rows_here && lane + 32 < S) ? __ldcg(p.lse_part + prow + lane + 32) : -INFINITY;
+    }
+    float4 v0[kDepth], v1[kDepth];
+    load_batch(0, slot, v0, v1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int row = warp + i * kConsumerWarps;
+        if (row >= rows_here) break;                              // warp-uniform
+        float M = fmaxf(l0[i], l1[i]);
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
+        const float w0 = l0[i] == -INFINITY ? 0.f : __expf(l0[i] - M);
+        const float w1 = l1[i] == -INFINITY ? 0.f : __expf(l1[i] - M);
+        float den = w0 + w1;
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o2);
+        const float inv = den > 0.f ? 1.f / den : 0.f;
+        sw[row * 64 + lane] = w0 * inv;
+        sw[row * 64 + lane + 32] = w1 * inv;
+        if (lane == 0 && p.lse_final != nullptr)
+            p.lse_final[(int64_t)b * p.Hq + h_base + row] = den > 0.f ? M + logf(den) : -INFINITY;
+    }
+    named_bar_sync(1, kConsumerWarps * 32);
+    for (int row = 0; row < rows_here; row += 2) {
+        const bool two = row + 1 < rows_here;
+        float4 a0 = zero4, a1 = zero4;
+        for (int s0 = slot; s0 < S; s0 += kSlots * kDepth) {
+            if (row != 0 || s0 != slot) load_batch(row, s0, v0, v1);
+#pragma unroll
+            for (int j = 0; j < kDepth; ++j) {
+                const int sp = s0 + j * kSlots;
+                const float w0 = sp < S ? sw[row * 64 + sp] : 0.f;
+                const float w1 = (two && sp < S) ? sw[(row + 1) * 64 + sp] : 0.f;
+                a0.x = fmaf(w0, v0[j].x, a0.x); a0.y = fmaf(w0, v0[j].y, a0.y);
+                a0.z = fmaf(w0, v0[j].z, a0.z); a0.w = fmaf(w0, v0[j].w, a0.w);
+                a1.x = fmaf(w1, v1[j].x, a1.x); a1.y = fmaf(w1, v1[j].y, a1.y);
+                a1.z = fmaf(w1, v1[j].z, a1.z); a1.w = fmaf(w1, v1[j].w, a1.w);
+            }
+        }
+        *reinterpret_cast<float4*>(&red[(slot * 16 + row) * kD + dv]) = a0;
+        if (two) *reinterpret_cast<float4*>(&red[(slot * 16 + row + 1) * kD + dv]) = a1;
+    }
+    named_bar_sync(1, kConsumerWarps * 32);
+    constexpr int kIlp = 4;
+    for (int base = tid; base < rows_here * kD; base += kIlp * kConsumerWarps * 32) {
+        float o[kIlp];
+#pragma unroll
+        for (int u = 0; u < kIlp; ++u) {
+            const int idx = min(base + u * kConsumerWarps * 32, rows_here * kD - 1);
+            const int row = idx / kD, d = idx - row * kD;
+            o[u] = 0.f;
+#pragma unroll
+            for (int sl = 0; sl < kSlots; ++sl) o[u] += red[(sl * 16 + row) * kD + d];
+        }
+#pragma unroll
+        for (int u = 0; u < kIlp; ++u) {
+            const int idx = base + u * kConsumerWarps * 32;
+            if (idx >= rows_here * kD) break;
+            const int row = idx / kD, d = idx - row * kD;
+            const elem_t val = from_f32<elem_t>(o[u]);
+            const int64_t off = b * p.osb + (h_base + row) * p.osh + d;
+            if (p.peer.n > 0) {
+                const int64_t poff = p.peer.base() + off;
+                for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[poff] = val;
+            } else {
+                reinterpret_cast<elem_t*>(p.o_final)[off] = val;
+            }
+        }
+    }
+}
 
 template <int kD, bool kBf16, bool kRows16>
 __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid_constant__ CUtensorMap map_k,
                                                                     const __grid_constant__ CUtensorMap map_v,
-                                                                    const DecodeTmaParams p) {
+                                                                    const __grid_constant__ DecodeTmaParams p) {
     constexpr int kHalves = kD / 64;
     constexpr int kSubTile = kStageTokens * 128;              // bytes of one [64 tok][64 el] sub-tile
     constexpr int kTileBytes = kHalves * kSubTile;            // K (or V) bytes per stage
@@ -218,41 +393,78 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x, b = blockIdx.z;
     const int hk = blockIdx.y % p.Hkv, hchunk = blockIdx.y / p.Hkv;   // hchunk: 16-row groups when G > 16
+    if (threadIdx.x == 0) PLI_DECODE_TRACE(0);                        // CTA start
+    // The parameter block spans several 64-byte lines of the constant bank; one lane per warp touches a line each, so
+    // that first-use misses later in the kernel (~600 cycles each) are all in flight together here.
+    {
+        constexpr int kLines = (int)((sizeof(DecodeTmaParams) + 63) / 64);
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(&p);
+        if (lane == 0) {
+            for (int l = warp; l < kLines; l += kConsumerWarps + kProducerWarps) {
+                const uint32_t v = words[l * 16];
+                asm volatile("" ::"r"(v));
+            }
+        }
+    }
+    // Start-up is a chain of dependent misses (sequence length -> block-table entries -> first TMA): shorten it.  A
+    // producer lane fetches the tensor maps first; the consumer threads, idle until the first stage lands, pull the
+    // part of this sequence's block-table row the CTA can touch towards L2 while the length is still in flight ...
+    if (threadIdx.x == kConsumerWarps * 32) {
+        prefetch_tensormap(&map_k);
+        prefetch_tensormap(&map_v);
+    }
+    if (p.table != nullptr && threadIdx.x < kConsumerWarps * 32) {
+        const int line = threadIdx.x * 32;                            // 32 entries = 128 bytes
+        if (line < p.table_stride) prefetch_l2(p.table + (int64_t)b * p.table_stride + line);
+    }
+    const int seq_len = p.seq_lens[b];                                // in flight; first used below
+    // ... and the producers read the block-table entries of their first stage for the split range the sequence would have
+    // at the host's max_seq_len (always right for a single split, right for every full-length sequence otherwise) without
+    // waiting for the length; a shorter sequence re-reads them once the length is known.
+    int t0_guess, t1_guess, page_guess = 0;
+    split_range_fast(p.max_len, p.S, p.fd_splits, s, t0_guess, t1_guess);
+    if (warp >= kConsumerWarps && p.table != nullptr) {
+        const int idx = (t0_guess + (lane << p.box_shift)) >> p.bs_shift;
+        if (lane < (kStageTokens >> p.box_shift) && idx < p.table_stride) page_guess = p.table[(int64_t)b * p.table_stride + idx];
+    }
     int t0, t1;
-    split_range(p.seq_lens[b], p.S, s, t0, t1);
+    split_range_fast(seq_len, p.S, p.fd_splits, s, t0, t1);
     const int n_stages = (t1 - t0 + kStageTokens - 1) / kStageTokens;
     const int rows_here = min(p.G - hchunk * 16, kRows16 ? 16 : 8);
     const int h_base = hk * p.G + hchunk * 16;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kDecodeStages; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], kProducerWarps);
             mbar_init(&empty_bar[i], kConsumerWarps);
         }
         fence_barrier_init();
     }
     __syncthreads();
+    if (threadIdx.x == 0) PLI_DECODE_TRACE(12);
     // programmatic dependent launch: the combine pass (launched with programmatic stream serialisation) may be
     // scheduled as soon as every CTA of this grid is running; it still waits for this grid's completion and memory
     // flush in its own griddepcontrol.wait, so only its launch latency is hidden.  No-op without a dependent.
     pdl_launch_dependents();
 
-    if (warp == kConsumerWarps) {
-        // ===================== producer warp: TMA page loads =====================
+    if (warp >= kConsumerWarps) {
+        // ===================== producer warps: TMA page loads (warp 4: K tiles, warp 5: V tiles) =====================
         if (n_stages > 0) {
-            if (lane == 0) {
-                prefetch_tensormap(&map_k);
-                prefetch_tensormap(&map_v);
-            }
-            const int boxes = kStageTokens / p.box_tokens;     // boxes (pages or sub-pages) per stage
+            const bool is_v = warp != kConsumerWarps;
+            const CUtensorMap* map = is_v ? &map_v : &map_k;
+            uint8_t* tiles = is_v ? v_tiles : k_tiles;
+            const int boxes = kStageTokens >> p.box_shift;     // boxes (pages or sub-pages) per stage
             const bool paged = p.table != nullptr;
             // lane i < boxes owns box i of every stage; its page id is fetched one stage ahead
             auto page_of = [&](int it) -> int {
-                const int t = t0 + it * kStageTokens + lane * p.box_tokens;
+                const int t = t0 + it * kStageTokens + (lane << p.box_shift);
                 if (!paged || lane >= boxes || t >= t1) return 0;
-                return p.table[(int64_t)b * p.table_stride + t / p.bs];
+                return p.table[(int64_t)b * p.table_stride + (t >> p.bs_shift)];
             };
-            int page_next = page_of(0);
+            int page_next = (t0 == t0_guess) ? page_guess : page_of(0);
+#if defined(PLI_TUNING) && PLI_TUNING
+            if (threadIdx.x == kConsumerWarps * 32 && page_next >= -0x7fffffff) PLI_DECODE_TRACE(13);   // (the compare makes the stamp wait for the load)
+#endif
             for (int it = 0; it < n_stages; ++it) {
                 const int slot = it % kDecodeStages;
                 const uint32_t parity = ((it / kDecodeStages) & 1) ^ 1;
@@ -261,23 +473,26 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 mbar_wait(&empty_bar[slot], parity);
                 // boxes that start at or beyond t1 are not loaded; consumers never read their smem as values
                 const int remaining = t1 - (t0 + it * kStageTokens);
-                const int live_boxes = min(boxes, (remaining + p.box_tokens - 1) / p.box_tokens);
+                const int live_boxes = min(boxes, (remaining + p.box_tokens - 1) >> p.box_shift);
                 if (lane == 0)
-                    mbar_arrive_expect_tx(&full_bar[slot], 2 * kHalves * live_boxes * p.box_tokens * 128);
+                    mbar_arrive_expect_tx(&full_bar[slot], (kHalves * live_boxes * 128) << p.box_shift);
                 __syncwarp();
+                if (it == 0 && threadIdx.x == kConsumerWarps * 32) PLI_DECODE_TRACE(6);        // about to issue the first loads
                 if (lane < live_boxes) {
-                    const int t = t0 + it * kStageTokens + lane * p.box_tokens;
+                    const int t = t0 + it * kStageTokens + (lane << p.box_shift);
                     // coordinates (d, head, slot, X, Y): paged (.., t % bs, layer, page); contiguous (.., t, 0, b)
-                    const int c2 = paged ? t % p.bs : t;
+                    const int c2 = paged ? (t & (p.bs - 1)) : t;
                     const int c3 = paged ? p.layer : 0;
                     const int c4 = paged ? page : b;
 #pragma unroll
                     for (int hf = 0; hf < kHalves; ++hf) {
-                        const int dst = slot * kTileBytes + hf * kSubTile + lane * p.box_tokens * 128;
-                        tma_load_5d(k_tiles + dst, &map_k, &full_bar[slot], hf * 64, hk, c2, c3, c4);
-                        tma_load_5d(v_tiles + dst, &map_v, &full_bar[slot], hf * 64, hk, c2, c3, c4);
+                        const int dst = slot * kTileBytes + hf * kSubTile + ((lane * 128) << p.box_shift);
+                        // K/V bytes are read once: evict-first, so that the block tables, lengths, queries and partials
+                        // every launch re-reads stay in L2 behind the stream
+                        tma_load_5d_hint(tiles + dst, map, &full_bar[slot], hf * 64, hk, c2, c3, c4, kL2EvictFirst);
                     }
                 }
+                if (it == 0 && threadIdx.x == kConsumerWarps * 32) PLI_DECODE_TRACE(1);        // first stage's loads issued
             }
         }
     } else {
@@ -322,6 +537,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         for (int it = 0; it < n_stages; ++it) {
             const int slot = it % kDecodeStages;
             mbar_wait(&full_bar[slot], (it / kDecodeStages) & 1);
+            if (it == 0 && threadIdx.x == 0) PLI_DECODE_TRACE(2);    // first stage landed
             const int tok_base = t0 + it * kStageTokens + warp * 16;
             const int n_valid = t1 - tok_base;                   // valid tokens in this warp's 16
             if (n_valid > 0) {
@@ -398,7 +614,10 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         }
 
         // ---- merge the four warps' partial softmax states through smem ----
+        if (threadIdx.x == 0) PLI_DECODE_TRACE(3);               // this warp's last stage consumed
+        if (lane == 0) PLI_DECODE_TRACE(8 + warp);
         named_bar_sync(1, kConsumerWarps * 32);                  // every stage consumed: ring is reusable
+        if (threadIdx.x == 0) PLI_DECODE_TRACE(14);
         float* mg_m = reinterpret_cast<float*>(smem);            // [4 warps][16 rows]
         float* mg_d = mg_m + 64;
         float* mg_o = mg_d + 64;                                 // [4 warps][16 rows][kD]
@@ -418,35 +637,67 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             }
         }
         named_bar_sync(1, kConsumerWarps * 32);
+        if (threadIdx.x == 0) PLI_DECODE_TRACE(15);
         const int tid = threadIdx.x;                             // 0..127
-        for (int idx = tid; idx < rows_here * kD; idx += kConsumerWarps * 32) {
-            const int row = idx / kD, d = idx - row * kD;
-            float M = -INFINITY;
+        // four elements per thread and pass, written as four independent chains (shared-memory reads, exp2, reciprocal,
+        // store): one element at a time was ~600 dependent cycles per element and warp, 2400 of a short kernel's tail
+        constexpr int kIlp = 4;
+        for (int base = tid; base < rows_here * kD; base += kIlp * kConsumerWarps * 32) {
+            float o_val[kIlp], lse_val[kIlp];
 #pragma unroll
-            for (int w = 0; w < 4; ++w) M = fmaxf(M, mg_m[w * 16 + row]);
-            float den = 0.f, o = 0.f;
+            for (int u = 0; u < kIlp; ++u) {
+                const int idx = min(base + u * kConsumerWarps * 32, rows_here * kD - 1);   // clamped: the store is guarded
+                const int row = idx / kD, d = idx - row * kD;
+                float M = -INFINITY;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float mw = mg_m[w * 16 + row];
-                const float wt = (mw == -INFINITY) ? 0.f : ex2_approx(mw - M);
-                den += wt * mg_d[w * 16 + row];
-                o += wt * mg_o[(w * 16 + row) * kD + d];
+                for (int w = 0; w < 4; ++w) M = fmaxf(M, mg_m[w * 16 + row]);
+                float den = 0.f, o = 0.f;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const float mw = mg_m[w * 16 + row];
+                    const float wt = (mw == -INFINITY) ? 0.f : ex2_approx(mw - M);
+                    den += wt * mg_d[w * 16 + row];
+                    o += wt * mg_o[(w * 16 + row) * kD + d];
+                }
+                o_val[u] = den > 0.f ? o / den : 0.f;
+                lse_val[u] = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
             }
-            const float o_val = den > 0.f ? o / den : 0.f;
-            const float lse_val = den > 0.f ? (M + log2f(den)) * kLn2 : -INFINITY;
-            if (p.peer.n > 0) {
-                const int64_t off = p.peer.base() + b * p.osb + (h_base + row) * p.osh + d;
-                const elem_t val = from_f32<elem_t>(o_val);
-                for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[off] = val;
-                if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val;
-            } else if (p.o_direct != nullptr) {
-                // single split: this CTA owns the whole sequence, so the combine pass is skipped
-                reinterpret_cast<elem_t*>(p.o_direct)[b * p.osb + (h_base + row) * p.osh + d] = from_f32<elem_t>(o_val);
-                if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val;
-            } else {
-                const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
-                p.o_part[prow * kD + d] = o_val;
-                if (d == 0) p.lse_part[prow] = lse_val;
+#pragma unroll
+            for (int u = 0; u < kIlp; ++u) {
+                const int idx = base + u * kConsumerWarps * 32;
+                if (idx >= rows_here * kD) break;
+                const int row = idx / kD, d = idx - row * kD;
+                if (p.o_direct != nullptr && p.peer.n > 0) {
+                    const int64_t off = p.peer.base() + b * p.osb + (h_base + row) * p.osh + d;
+                    const elem_t val = from_f32<elem_t>(o_val[u]);
+                    for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[off] = val;
+                    if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val[u];
+                } else if (p.o_direct != nullptr) {
+                    // single split: this CTA owns the whole sequence, so the combine pass is skipped
+                    reinterpret_cast<elem_t*>(p.o_direct)[b * p.osb + (h_base + row) * p.osh + d] = from_f32<elem_t>(o_val[u]);
+                    if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val[u];
+                } else {
+                    const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
+                    p.o_part[prow * kD + d] = o_val[u];
+                    if (d == 0) p.lse_part[prow] = lse_val[u];
+                }
+            }
+        }
+        if (threadIdx.x == 0) PLI_DECODE_TRACE(4);               // output / partial written
+        if (p.counters != nullptr) {
+            // ---- fused combine: the last split of this unit to arrive merges all of them ----
+            // (the partial stores of all 128 threads happen before thread 0's release through the CTA barrier; the merge
+            // reads the partials with ld.global.cg, i.e. from L2, after the barrier that follows thread 0's acquire)
+            int* is_last = reinterpret_cast<int*>(empty_bar + kDecodeStages);
+            named_bar_sync(1, kConsumerWarps * 32);
+            unsigned long long* ctr = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);
+            bool tagged = false;
+            if (tid == 0) *is_last = unit_arrive(ctr, p.launch_id, tagged) == (uint32_t)p.S - 1u;
+            named_bar_sync(1, kConsumerWarps * 32);
+            if (*is_last) {
+                combine_unit<kD, elem_t>(p, reinterpret_cast<float*>(smem), b, h_base, rows_here, tid);
+                if (tid == 0) unit_reset(ctr, p.launch_id, tagged);
+                if (threadIdx.x == 0) PLI_DECODE_TRACE(5);       // combined output written
             }
         }
     }
@@ -607,6 +858,19 @@ __global__ void paged_gather_kernel(const T* __restrict__ store, T* __restrict__
 // host launchers
 // ------------------------------------------------------------------------------------------------
 bool is_pow2(int x) { return x > 0 && (x & (x - 1)) == 0; }
+int ilog2(int x) { int l = 0; while ((1 << (l + 1)) <= x) ++l; return l; }
+
+// Id of a split-KV launch (see unit_arrive): distinct for distinct launches of this process, never 0.
+uint32_t next_launch_id() {
+    static std::atomic<uint32_t> id{0x9E3779B9u};
+    uint32_t v = id.fetch_add(1u, std::memory_order_relaxed) + 1u;
+    return v ? v : id.fetch_add(1u, std::memory_order_relaxed) + 1u;
+}
+
+#if defined(PLI_TUNING) && PLI_TUNING
+unsigned long long* g_decode_trace = nullptr;   // process-wide, unsynchronised: tuning builds are driven from one thread
+int g_decode_trace_cap = 0;
+#endif
 
 bool tma_eligible(int D, int dtype, int block_size, bool paged, const int64_t* st, const void* k, const void* v) {
     if (dtype != PLI_BF16 && dtype != PLI_F16) return false;
@@ -644,7 +908,7 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
     auto kern = decode_tma_kernel<kD, kBf16, kRows16>;
     constexpr int kTileBytes = (kD / 64) * kStageTokens * 128;
     const size_t merge_bytes = (size_t)(128 + 64 * kD) * sizeof(float);
-    size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 1024;
+    size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 16 + 1024;
     if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, (int)smem));
     PLI_CUDA_CHECK(bind_status_symbol());
@@ -661,6 +925,22 @@ cudaError_t bind_status_decode() { return bind_status_symbol(); }
 }  // namespace pli
 
 using namespace pli;
+
+// Tuning builds: 16 x uint64 per CTA of the next TMA split-KV launches: SM clock stamps (0 start, 1 first loads issued,
+// 2 first stage landed, 3 last stage consumed, 4 output / partial written, 5 merged output written, 8-11 last stage
+// consumed by consumer warp 0-3, 12 barriers initialised, 13 first page ids known, 14 / 15 first / second barrier of the
+// cross-warp merge passed) and, in word 7, the %globaltimer at the start (to place CTAs against each other); (NULL, 0)
+// switches it off.  tools/decode_trace.py.
+extern "C" int pli_debug_decode_trace(void* buf, int cap_ctas) {
+#if defined(PLI_TUNING) && PLI_TUNING
+    g_decode_trace = static_cast<unsigned long long*>(buf);
+    g_decode_trace_cap = buf ? cap_ctas : 0;
+    return PLI_OK;
+#else
+    (void)buf; (void)cap_ctas;
+    return set_error(PLI_ERR_UNSUPPORTED, "pli_debug_decode_trace is compiled into tuning builds only");
+#endif
+}
 
 extern "C" int pli_decode_num_splits(int B, int Hkv, int max_seq_len) {
     if (B <= 0 || Hkv <= 0 || max_seq_len <= 0) return 1;
@@ -680,9 +960,15 @@ extern "C" int pli_decode_num_splits(int B, int Hkv, int max_seq_len) {
     return s;
 }
 
+// Workspace: [B*Hq*S*D] partial outputs (f32), [B*Hq*S] partial LSEs (f32), then -- 8-byte aligned -- B*Hq arrival counter
+// pairs (one per (b, kv head, 16-row chunk) is used) for the combine fused into the split-KV kernel.  Nothing needs
+// initialising (unit_arrive).
+static size_t partials_bytes(int B, int Hq, int D, int num_splits) {
+    return (((size_t)B * Hq * num_splits * (size_t)(D + 1) * sizeof(float)) + 7) & ~(size_t)7;
+}
 extern "C" size_t pli_decode_workspace_bytes(int B, int Hq, int D, int num_splits) {
     if (B <= 0 || Hq <= 0 || D <= 0 || num_splits <= 0) return 0;
-    return (size_t)B * Hq * num_splits * (size_t)(D + 1) * sizeof(float);
+    return partials_bytes(B, Hq, D, num_splits) + (size_t)B * Hq * 2 * sizeof(unsigned long long);
 }
 
 extern "C" int pli_decode_kernel_kind(int D, int dtype, int block_size, const int64_t kv_strides[4], const void* k_store,
@@ -699,7 +985,7 @@ static int check_decode_args(const void* q, const void* k, const void* v, const 
     if (D > 256) return set_error(PLI_ERR_UNSUPPORTED, "head_dim %d > 256", D);
     if (max_seq_len <= 0) return set_error(PLI_ERR_INVALID, "max_seq_len must be positive");
     if (paged && block_size <= 0) return set_error(PLI_ERR_INVALID, "block_size must be positive for paged KV");
-    if (num_splits <= 0) return set_error(PLI_ERR_INVALID, "num_splits must be positive");
+    if (num_splits <= 0 || num_splits > 64) return set_error(PLI_ERR_INVALID, "num_splits must be in [1, 64]");
     if (B > 65535) return set_error(PLI_ERR_UNSUPPORTED, "B > 65535");
     return PLI_OK;
 }
@@ -735,17 +1021,33 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
                          box_tokens);
         if (rc) return rc;
         DecodeTmaParams p;
+#if defined(PLI_TUNING) && PLI_TUNING
+        p.trace = g_decode_trace;
+        p.trace_cap = g_decode_trace_cap;
+#else
+        p.trace = nullptr;
+        p.trace_cap = 0;
+#endif
         p.q = q;
         p.table = block_table;
         p.seq_lens = seq_lens;
         p.o_part = o_part;
         p.lse_part = lse_part;
+        // with an output given, this one launch produces it: a single split writes it straight away, several splits are
+        // merged by the last CTA of each unit to arrive (fused combine)
         const bool direct = o_direct != nullptr && num_splits == 1;
+        const bool fused = o_direct != nullptr && num_splits > 1 && num_splits <= 64;
         p.o_direct = direct ? o_direct : nullptr;
         p.lse_direct = direct ? lse_direct : nullptr;
-        p.osb = direct ? o_strides[0] : 0;
-        p.osh = direct ? o_strides[1] : 0;
-        if (wrote_direct) *wrote_direct = direct;
+        p.osb = (direct || fused) ? o_strides[0] : 0;
+        p.osh = (direct || fused) ? o_strides[1] : 0;
+        p.counters = fused ? reinterpret_cast<unsigned long long*>(static_cast<char*>(workspace) +
+                                                                    partials_bytes(B, Hq, D, num_splits))
+                           : nullptr;
+        p.launch_id = next_launch_id();
+        p.o_final = fused ? o_direct : nullptr;
+        p.lse_final = fused ? lse_direct : nullptr;
+        if (wrote_direct) *wrote_direct = direct || fused;
         p.qsb = q_strides[0];
         p.qsh = q_strides[1];
         p.Hq = Hq;
@@ -756,9 +1058,13 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
         p.layer = layer;
         p.S = num_splits;
         p.box_tokens = box_tokens;
+        p.max_len = max_seq_len;
+        p.bs_shift = ilog2(p.bs);
+        p.box_shift = ilog2(box_tokens);
+        p.fd_splits = make_fastdiv((uint32_t)num_splits);
         p.scale_log2 = scale * kLog2e;
         p.peer = PeerScatter{};
-        if (direct && peer != nullptr) p.peer = *peer;
+        if ((direct || fused) && peer != nullptr) p.peer = *peer;
         const int hchunks = (G + 15) / 16;
         dim3 grid(num_splits, Hkv * hchunks, B);
         const bool rows16 = G > 8;

@@ -112,26 +112,6 @@ struct SmemLayout {
 // p = 31 + ceil(log2 d); exact for dividends below 2^31).  decode_item runs once per work item in EVERY warp role, and
 // its six integer divisions, each a ~150-cycle dependent chain on a GPU without a divider, were ~1500 serial cycles per
 // item and role (in-kernel timeline at N = 512: every role idled that long between items).
-struct FastDiv {
-    uint32_t d, mul, sh;
-    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : (__umulhi(n, mul) >> sh); }
-    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
-        q = div(n);
-        r = n - q * d;
-    }
-};
-inline FastDiv make_fastdiv(uint32_t d) {
-    FastDiv f{d ? d : 1u, 0u, 0u};
-    if (f.d > 1) {
-        uint32_t l = 0;
-        while ((1ull << l) < f.d) ++l;
-        const uint32_t pw = 31 + l;
-        f.mul = (uint32_t)(((1ull << pw) + f.d - 1) / f.d);
-        f.sh = pw - 32;
-    }
-    return f;
-}
-
 struct PrefillParams {
     float* lse;
     int B, Hq, Hkv, Nq, Nk;

@@ -312,3 +312,70 @@ def test_decode_plan_matches_flash_decode_and_replays_in_a_graph():
     assert torch.equal(out.unsqueeze(2), pli.flash_decode(qd, kd, vd, ld, block_tables=td, max_seq_len=1024))
     with pytest.raises(TypeError):
         pli.DecodePlan(qd, kd, vd, 300, block_tables=td)
+
+
+@pytest.mark.parametrize("B,G,D,L,splits", [(1, 4, 128, 32768, 37), (3, 8, 64, 5000, 64), (2, 16, 128, 2000, 5),
+                                            (4, 32, 128, 777, 3)])
+def test_fused_combine_matches_the_two_pass_path_on_a_dirty_workspace(B, G, D, L, splits):
+    """Several splits per sequence: the split-KV kernel's last-arriving CTA of every unit merges the partials itself (no
+    combine launch).  Its arrival counters live in the caller's workspace and need no initialisation: the same answer
+    from a workspace full of 0xFF bytes / random bits / the previous launch's state, under CUDA-graph replay too, and
+    equal (to fp32 rounding of the merge order) to the two-pass C-ABI path pli_decode_splitkv + pli_decode_combine."""
+    from physics_llm_inference_b200 import _lib
+    Hkv, bs = 2, 16
+    Hq = Hkv * G
+    lens_l = [L] + [max(1, L // (i + 2)) for i in range(B - 1)]
+    q, kp, vp, table, lens = orc.seeded_paged(91, B, Hq, Hkv, D, bs, lens_l, dtype=torch.bfloat16)
+    qd, kd, vd, td, ld = q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens.cuda()
+    lib = _lib.load()
+    need = int(lib.pli_decode_workspace_bytes(B, Hq, D, splits))
+    # two-pass reference through the C ABI
+    ws2 = torch.empty(need // 4 + 2, dtype=torch.float32, device="cuda")
+    o2 = torch.empty(B, Hq, D, device="cuda", dtype=torch.bfloat16)
+    l2 = torch.empty(B, Hq, device="cuda", dtype=torch.float32)
+    stream = torch.cuda.current_stream().cuda_stream
+    q3 = qd[:, :, 0, :]
+    _lib.check(lib.pli_decode_splitkv(q3.data_ptr(), kd.data_ptr(), vd.data_ptr(), td.data_ptr(), ld.data_ptr(), B, Hq, Hkv, D,
+                                      L, bs, td.stride(0), 0, kd.shape[0], _lib.i64(q3.stride(0), q3.stride(1)),
+                                      _lib.i64(*kd.stride()[:4]), D ** -0.5, _lib.dtype_code(qd.dtype), splits,
+                                      ws2.data_ptr(), ws2.numel() * 4, stream))
+    _lib.check(lib.pli_decode_combine(ws2.data_ptr(), o2.data_ptr(), l2.data_ptr(), B, Hq, D, splits,
+                                      _lib.i64(o2.stride(0), o2.stride(1)), _lib.dtype_code(qd.dtype), stream))
+    ro, rlse = orc.paged_decode_oracle(qd, kd, vd, table, lens)
+    assert (o2.float().cpu().unsqueeze(2) - ro).abs().max().item() <= 2e-2
+    launches = pli.launch_count()
+    for fill in ("ff", "random", "reuse", "reuse"):
+        ws = torch.empty(need // 4 + 2, dtype=torch.float32, device="cuda")
+        if fill == "ff":
+            ws.view(torch.uint8).fill_(0xFF)
+        elif fill == "random":
+            ws.view(torch.int32).random_(-2**31, 2**31 - 1)
+        else:
+            ws = prev_ws                                              # noqa: F821  (state left by the previous launch)
+        out = torch.full((B, Hq, D), float("nan"), device="cuda", dtype=torch.bfloat16)
+        o, lse = pli.flash_decode(qd, kd, vd, ld, block_tables=td, max_seq_len=L, num_splits=splits, workspace=ws, out=out,
+                                  return_lse=True)
+        torch.cuda.synchronize()
+        assert (o.float() - o2.float().unsqueeze(2)).abs().max().item() <= 1e-2 * o2.float().abs().max().item() + 1e-3, fill
+        assert (lse - l2).abs().max().item() <= 1e-4, fill
+        assert (lse.cpu() - rlse[:, :, 0]).abs().max().item() <= LSE_TOL
+        prev_ws = ws                                                  # noqa: F841
+    assert pli.launch_count() - launches == 4, "one launch per fused call (no combine pass)"
+    # graph replays: the launch id is frozen in the graph, the last arriver leaves zero arrivals behind
+    plan = pli.DecodePlan(qd, kd, vd, ld, block_tables=td, max_seq_len=L, num_splits=splits, workspace=prev_ws, out=out)
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            plan()
+            plan()
+    torch.cuda.current_stream().wait_stream(side)
+    first = out.clone()
+    for _ in range(3):
+        out.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, first)
