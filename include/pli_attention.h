@@ -139,10 +139,15 @@ int pli_prefill_kernel_kind(int D, int dtype, const int64_t q_strides[3], const 
  *       paged:       {page, layer, slot, head}      contiguous: {batch, 0, token, head}
  *   kv_extent = number of pages in the pool (paged) or B (contiguous): bounds for TMA descriptors.
  *   max_seq_len = upper bound of seq_lens (host value; no device sync is done to find it).
- *   num_splits  = KV splits per (b, kv head); pass 0 to let the library pick
- *                 (pli_decode_num_splits); workspace must hold pli_decode_workspace_bytes().
+ *   num_splits  = KV splits per (b, kv head), 1..64; pass 0 to let the library pick
+ *                 (pli_decode_num_splits); workspace must hold pli_decode_workspace_bytes() and
+ *                 needs NO initialisation (it carries the partials and, behind them, one arrival
+ *                 counter pair per (b, kv head) that tolerates any previous contents).
  *
- * pli_decode_fwd = pli_decode_splitkv (partials into workspace) + pli_decode_combine.
+ * pli_decode_fwd is ONE launch on the TMA path (bf16 / f16, head_dim 64 / 128): with several splits the
+ * CTA of a (b, kv head) that finishes last merges that unit's partials itself.  pli_decode_splitkv
+ * (partials into workspace) + pli_decode_combine is the same computation as two launches, and what
+ * pli_decode_fwd does on the SIMT path.
  * ------------------------------------------------------------------------------------------- */
 int pli_decode_num_splits(int B, int Hkv, int max_seq_len);
 size_t pli_decode_workspace_bytes(int B, int Hq, int D, int num_splits);
@@ -195,6 +200,9 @@ typedef struct pli_peer_scatter {
     uint32_t* epoch;
     int64_t buffer_stride;
     int64_t slice_offset;
+    /* pli_decode_fwd_gather only (may be NULL for the calls above): */
+    uint32_t* peer_ready[PLI_MAX_PEERS];   /* rank r's array of n_peers zero-initialised "ready to receive" words */
+    uint32_t* cta_counter;                 /* LOCAL zero-initialised device word (CTAs of the running grid that finished) */
 } pli_peer_scatter;
 int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
                            const int32_t* seq_lens, float* lse, int B, int Hq, int Hkv, int D, int max_seq_len,
@@ -203,6 +211,26 @@ int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_sto
                            float scale, int dtype, int num_splits, void* workspace, size_t workspace_bytes,
                            const pli_peer_scatter* ps, void* stream);
 int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream);
+
+/* The same gather as ONE call and ONE output buffer per rank (buffer_stride must be 0; the output address never changes,
+ * so the step captures into a CUDA graph next to its consumers without a copy).  The publish / wait kernel is launched by
+ * this call, programmatically behind the decode grid (no launch latency).  Two credits replace the second buffer:
+ *   peer_ready[r][rank] = e  is raised by this rank's kernel of step e when it STARTS (stream order: everything that read
+ *                            this rank's buffer of step e-1 is complete), and a CTA stores into rank r's buffer only after
+ *                            it has seen peer_ready[rank][r] >= e;
+ *   peer_flags[r][rank] = e  is published once the decode grid is complete (the whole slice has been stored); the stream
+ *                            then waits for peer_flags[rank][r] >= e for all r and *epoch advances.
+ * Same arguments as pli_decode_fwd_scatter; served by the TMA kernel only (bf16 / f16, head_dim 64 / 128, page size a power
+ * of two): PLI_ERR_UNSUPPORTED otherwise, before anything is launched.  Stream contract: the kernels that read the output of
+ * step e are enqueued before step e+1 on the same stream (or ordered before it by an event).  A peer that does not show up
+ * within pli_set_peer_timeout_ms is reported through pli_device_status, not trapped.
+ * (ch09/nccl_primitives.py:45-67 is the reference's cost model of the all-gather this replaces.) */
+int pli_decode_fwd_gather(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                          const int32_t* seq_lens, float* lse, int B, int Hq, int Hkv, int D, int max_seq_len,
+                          int block_size, int table_stride, int layer, int64_t kv_extent,
+                          const int64_t q_strides[2], const int64_t kv_strides[4], const int64_t o_strides[2],
+                          float scale, int dtype, int num_splits, void* workspace, size_t workspace_bytes,
+                          const pli_peer_scatter* ps, void* stream);
 
 /* Copy the output buffer written by the step that has just completed on this stream (its parity is read from the device
  * step counter) into a FIXED destination of `nbytes` bytes (elements of `elem_size` bytes).  Needed under CUDA-graph

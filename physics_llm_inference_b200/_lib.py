@@ -28,7 +28,8 @@ class PeerScatter(C.Structure):
     """`pli_peer_scatter` of include/pli_attention.h."""
     _fields_ = [("n_peers", C.c_int32), ("rank", C.c_int32), ("peer_o", C.c_void_p * PLI_MAX_PEERS),
                 ("peer_flags", C.c_void_p * PLI_MAX_PEERS), ("epoch", C.c_void_p),
-                ("buffer_stride", C.c_int64), ("slice_offset", C.c_int64)]
+                ("buffer_stride", C.c_int64), ("slice_offset", C.c_int64),
+                ("peer_ready", C.c_void_p * PLI_MAX_PEERS), ("cta_counter", C.c_void_p)]
 
 
 _SIGNATURES = {
@@ -59,6 +60,9 @@ _SIGNATURES = {
     "pli_decode_fwd_scatter": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_int, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_float, C.c_int,
                                          C.c_int, _VP, C.c_size_t, C.POINTER(PeerScatter), _VP]),
+    "pli_decode_fwd_gather": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, C.c_int64, _I64P, _I64P, _I64P, C.c_float, C.c_int,
+                                        C.c_int, _VP, C.c_size_t, C.POINTER(PeerScatter), _VP]),
     "pli_prefill_fwd_scatter": (C.c_int, [_VP, _VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           _I64P, _I64P, _I64P, _I64P, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.POINTER(PeerScatter), _VP]),

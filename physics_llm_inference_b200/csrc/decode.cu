@@ -207,6 +207,50 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 #define PLI_DECODE_TRACE(slot) do { } while (0)
 #endif
 
+// Spin (acquire, system scope) until *w has reached e.  A peer that is merely late is waited for: the bound is WALL time
+// (pli_set_peer_timeout_ms; 0 = forever); false when it expired.
+__device__ __forceinline__ bool wait_flag_reaches(const uint32_t* w, uint32_t e, unsigned long long timeout_ns) {
+    uint64_t t0 = 0;
+    for (uint32_t spin = 1; (int32_t)(ld_acquire_sys(w) - e) < 0; ++spin) {
+        __nanosleep(32);
+        if ((spin & 0x3FFu) == 0 && timeout_ns != 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > timeout_ns) return false;
+        }
+    }
+    return true;
+}
+// A peer did not show up in time: no trap -- (this rank, the missing rank, the step) go into the host-visible fault
+// record, which pli_device_status / PeerOutput turn into an error on the host, and the stream continues.
+__device__ __forceinline__ void record_peer_timeout(unsigned long long* status, int rank, int missing, uint32_t e) {
+    if (status == nullptr) return;
+    status[1] = ((unsigned long long)rank << 32) | (unsigned)missing;
+    status[2] = e;
+    status[3] = global_timer_ns();
+    __threadfence_system();
+    status[0] = PLI_FAULT_PEER_TIMEOUT;
+    __threadfence_system();
+}
+
+// Single-launch gather (pli_decode_fwd_gather): ONE output buffer per rank and a credit in each direction.
+//   ready[r][me] = e   written by me into rank r's memory when my kernel of step e STARTS: everything on my stream that read
+//                      my buffer's step e-1 contents is complete, rank r may overwrite its slice of it;
+//   done[r][me]  = e   written by me into rank r's memory when all of my slice of step e has landed there.
+// A CTA stores into rank r's buffer only after it has seen ready[me][r] >= e (polled by a producer warp while the K/V
+// stream runs, handed to the consumers through an mbarrier); the last CTA of the grid to finish publishes done, waits for
+// every peer's done and advances *epoch.  No rank ever waits for something that depends on its own progress in step e,
+// so this cannot deadlock as long as every rank launches step e.
+struct PeerGather {
+    uint32_t* done[PLI_MAX_PEERS];
+    uint32_t* ready[PLI_MAX_PEERS];
+    uint32_t* epoch;                  // LOCAL: steps completed
+    uint32_t* cta_counter;            // LOCAL: CTAs of the running grid that have finished (zero between launches)
+    int n, rank;                      // n == 0: not a single-launch gather
+    unsigned long long timeout_ns;
+    unsigned long long* status;
+};
+
 struct DecodeTmaParams {
     unsigned long long* trace;   // tuning builds: 16 timestamps per CTA (pli_debug_decode_trace), else NULL
     int trace_cap;
@@ -230,6 +274,7 @@ struct DecodeTmaParams {
     uint32_t launch_id;
     void* o_final;                  // with osb / osh; unused when peer.n > 0
     float* lse_final;               // or NULL
+    PeerGather gather;
 };
 
 // Arrival of one split's CTA on its unit's counter pair; returns the number of arrivals before this one.
@@ -348,6 +393,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
     uint8_t* v_tiles = smem + kDecodeStages * kTileBytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(v_tiles + kDecodeStages * kTileBytes);
     uint64_t* empty_bar = full_bar + kDecodeStages;
+    uint64_t* peer_ok = empty_bar + kDecodeStages + 1;        // (empty_bar[kDecodeStages] is the is_last word)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x, b = blockIdx.z;
@@ -376,6 +422,13 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         const int line = threadIdx.x * 32;                            // 32 entries = 128 bytes
         if (line < p.table_stride) prefetch_l2(p.table + (int64_t)b * p.table_stride + line);
     }
+    // single-launch gather: this rank's kernel of step e has started, so its output buffer may be overwritten
+    uint32_t step = 0;
+    if (p.gather.n > 0) {
+        step = *p.gather.epoch + 1u;
+        if (blockIdx.x + blockIdx.y + blockIdx.z == 0 && warp == kConsumerWarps && lane < p.gather.n)
+            st_release_sys(p.gather.ready[lane] + p.gather.rank, step);
+    }
     const int seq_len = p.seq_lens[b];                                // in flight; first used below
     // ... and the producers read the block-table entries of their first stage for the split range the sequence would have
     // at the host's max_seq_len (always right for a single split, right for every full-length sequence otherwise) without
@@ -397,6 +450,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             mbar_init(&full_bar[i], kProducerWarps);
             mbar_init(&empty_bar[i], kConsumerWarps);
         }
+        mbar_init(peer_ok, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -453,6 +507,14 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 }
                 if (it == 0 && threadIdx.x == kConsumerWarps * 32) PLI_DECODE_TRACE(1);        // first stage's loads issued
             }
+        }
+        if (p.gather.n > 0 && warp == kConsumerWarps) {
+            // every peer ready to receive step e?  (normally long true: they raised it when their kernels started)
+            if (lane < p.gather.n &&
+                !wait_flag_reaches(p.gather.ready[p.gather.rank] + lane, step, p.gather.timeout_ns))
+                record_peer_timeout(p.gather.status, p.gather.rank, lane, step);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(peer_ok);
         }
     } else {
         // ===================== consumer warps =====================
@@ -601,6 +663,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         const int tid = threadIdx.x;                             // 0..127
         // four elements per thread and pass, written as four independent chains (shared-memory reads, exp2, reciprocal,
         // store): one element at a time was ~600 dependent cycles per element and warp, 2400 of a short kernel's tail
+        if (p.gather.n > 0 && p.o_direct != nullptr) mbar_wait(peer_ok, 0);      // the peers' buffers may be written
         constexpr int kIlp = 4;
         for (int base = tid; base < rows_here * kD; base += kIlp * kConsumerWarps * 32) {
             float o_val[kIlp], lse_val[kIlp];
@@ -657,9 +720,36 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             if (tid == 0) *is_last = unit_arrive(ctr, p.launch_id, tagged) == (uint32_t)p.S - 1u;
             named_bar_sync(1, kConsumerWarps * 32);
             if (*is_last) {
+                if (p.gather.n > 0) mbar_wait(peer_ok, 0);
                 combine_unit<kD, elem_t>(p, b, h_base, rows_here, tid);
                 if (tid == 0) unit_reset(ctr, p.launch_id, tagged);
                 if (threadIdx.x == 0) PLI_DECODE_TRACE(5);       // combined output written
+            }
+        }
+        if (p.gather.n > 0 && p.gather.cta_counter != nullptr) {
+            // ---- (option, off: see pli_decode_fwd_gather) the last CTA of the grid to get here publishes this rank's
+            // slice and waits for the peers' ----
+            named_bar_sync(1, kConsumerWarps * 32);              // every consumer thread's peer stores are issued
+            if (warp == 0) {
+                uint32_t last = 0;
+                if (lane == 0) {
+                    __threadfence_system();                      // ... and visible system-wide before this CTA counts
+                    last = atomicAdd(p.gather.cta_counter, 1u) == gridDim.x * gridDim.y * gridDim.z - 1u;
+                    if (last) {
+                        *p.gather.cta_counter = 0u;              // zero for the next launch / graph replay
+                        __threadfence_system();                  // acquire side of the other CTAs' fence + arrival
+                    }
+                }
+                last = __shfl_sync(0xffffffffu, last, 0);
+                if (last) {
+                    if (lane < p.gather.n) {
+                        st_release_sys(p.gather.done[lane] + p.gather.rank, step);
+                        if (!wait_flag_reaches(p.gather.done[p.gather.rank] + lane, step, p.gather.timeout_ns))
+                            record_peer_timeout(p.gather.status, p.gather.rank, lane, step);
+                    }
+                    __syncwarp();
+                    if (lane == 0) *p.gather.epoch = step;       // the step is complete on this rank
+                }
             }
         }
     }
@@ -734,31 +824,13 @@ __global__ void __launch_bounds__(128) decode_combine_kernel(const float* o_part
 // turn into an error on the host, and lets the stream continue (the step's output is then incomplete).
 __global__ void peer_publish_wait_kernel(const PeerFlags pf) {
     const int r = threadIdx.x;
+    pdl_wait();                       // launched programmatically behind the storing grid: it is complete and flushed now
     const uint32_t e = *pf.epoch + 1u;
     __syncwarp();
     if (r < pf.n) {
         __threadfence_system();
         st_release_sys(pf.flags[r] + pf.rank, e);
-        const uint32_t* mine = pf.flags[pf.rank] + r;
-        uint64_t t0 = 0;
-        for (uint32_t spin = 1; (int32_t)(ld_acquire_sys(mine) - e) < 0; ++spin) {
-            __nanosleep(32);
-            if ((spin & 0x3FFu) == 0 && pf.timeout_ns != 0) {
-                const uint64_t now = global_timer_ns();
-                if (t0 == 0) t0 = now;
-                else if (now - t0 > pf.timeout_ns) {
-                    if (pf.status != nullptr) {
-                        pf.status[1] = ((unsigned long long)pf.rank << 32) | (unsigned)r;       // waiting rank | missing rank
-                        pf.status[2] = e;
-                        pf.status[3] = now;
-                        __threadfence_system();
-                        pf.status[0] = PLI_FAULT_PEER_TIMEOUT;
-                        __threadfence_system();
-                    }
-                    break;
-                }
-            }
-        }
+        if (!wait_flag_reaches(pf.flags[pf.rank] + r, e, pf.timeout_ns)) record_peer_timeout(pf.status, pf.rank, r, e);
     }
     __syncwarp();
     if (r == 0) *pf.epoch = e;        // the step is complete on this rank
@@ -952,6 +1024,18 @@ static int check_decode_args(const void* q, const void* k, const void* v, const 
     return PLI_OK;
 }
 
+#ifndef PLI_PUBLISH_FROM_LAST_CTA
+#define PLI_PUBLISH_FROM_LAST_CTA 0
+#endif
+static constexpr bool kPublishFromLastCta = PLI_PUBLISH_FROM_LAST_CTA != 0;
+
+// The TMA + mma.sync kernel serves this call (else: the SIMT kernel).
+static bool tma_path_ok(const void* q, const void* k_store, const void* v_store, int D, int dtype, int block_size, bool paged,
+                        const int64_t q_strides[2], const int64_t kv_strides[4], float scale) {
+    return scale > 0.f && tma_eligible(D, dtype, block_size, paged, kv_strides, k_store, v_store) && (q_strides[0] % 2 == 0) &&
+           (q_strides[1] % 2 == 0) && ((reinterpret_cast<uintptr_t>(q) & 3) == 0);
+}
+
 // Split-KV launch.  When o_direct is given, num_splits == 1 and the TMA kernel serves the request,
 // the kernel writes the final output itself and *wrote_direct is set (the combine pass is not needed).
 static int splitkv_impl(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
@@ -959,7 +1043,8 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
                         int table_stride, int layer, int64_t kv_extent, const int64_t q_strides[2],
                         const int64_t kv_strides[4], float scale, int dtype, int num_splits, void* workspace,
                         size_t workspace_bytes, cudaStream_t stream, void* o_direct, float* lse_direct,
-                        const int64_t* o_strides, bool* wrote_direct, const PeerScatter* peer = nullptr) {
+                        const int64_t* o_strides, bool* wrote_direct, const PeerScatter* peer = nullptr,
+                        const PeerGather* gather = nullptr) {
     const bool paged = block_table != nullptr;
     if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
     int rc = check_decode_args(q, k_store, v_store, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, paged, num_splits);
@@ -971,8 +1056,7 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
     float* lse_part = o_part + (size_t)B * Hq * num_splits * D;
     const int G = Hq / Hkv;
 
-    if (scale > 0.f && tma_eligible(D, dtype, block_size, paged, kv_strides, k_store, v_store) && (q_strides[0] % 2 == 0) &&
-        (q_strides[1] % 2 == 0) && ((reinterpret_cast<uintptr_t>(q) & 3) == 0)) {
+    if (tma_path_ok(q, k_store, v_store, D, dtype, block_size, paged, q_strides, kv_strides, scale)) {
         const int box_tokens = paged ? (block_size < kStageTokens ? block_size : kStageTokens) : kStageTokens;
         // layers extent: the layer coordinate must be inside the tensor; layer+1 is a safe lower bound
         CUtensorMap mk, mv;
@@ -1009,6 +1093,8 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
         p.launch_id = next_launch_id();
         p.o_final = fused ? o_direct : nullptr;
         p.lse_final = fused ? lse_direct : nullptr;
+        p.gather = PeerGather{};
+        if ((direct || fused) && peer != nullptr && gather != nullptr) p.gather = *gather;
         if (wrote_direct) *wrote_direct = direct || fused;
         p.qsb = q_strides[0];
         p.qsh = q_strides[1];
@@ -1160,6 +1246,73 @@ extern "C" int pli_decode_fwd_scatter(const void* q, const void* k_store, const 
     if (rc) return rc;
     if (wrote_direct) return PLI_OK;
     return combine_impl(workspace, nullptr, lse, B, Hq, D, num_splits, o_strides, dtype, stream, peer);
+}
+
+extern "C" int pli_decode_fwd_gather(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
+                                     const int32_t* seq_lens, float* lse, int B, int Hq, int Hkv, int D, int max_seq_len,
+                                     int block_size, int table_stride, int layer, int64_t kv_extent,
+                                     const int64_t q_strides[2], const int64_t kv_strides[4], const int64_t o_strides[2],
+                                     float scale, int dtype, int num_splits, void* workspace, size_t workspace_bytes,
+                                     const pli_peer_scatter* ps, void* stream) {
+    if (!ps || !o_strides || !q_strides || !kv_strides) return set_error(PLI_ERR_INVALID, "null argument");
+    if (ps->n_peers < 1 || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
+    if (ps->rank < 0 || ps->rank >= ps->n_peers) return set_error(PLI_ERR_INVALID, "rank outside [0, n_peers)");
+    if (!ps->epoch || !ps->cta_counter) return set_error(PLI_ERR_INVALID, "null epoch / cta_counter word");
+    if (ps->buffer_stride != 0)
+        return set_error(PLI_ERR_INVALID, "the single-launch gather writes ONE buffer per rank: buffer_stride must be 0");
+    if (!tma_path_ok(q, k_store, v_store, D, dtype, block_size, block_table != nullptr, q_strides, kv_strides, scale))
+        return set_error(PLI_ERR_UNSUPPORTED, "this storage is served by the SIMT kernel: use pli_decode_fwd_scatter + "
+                                              "pli_peer_publish_wait (two buffers)");
+    PeerScatter peer{};
+    PeerGather gather{};
+    for (int r = 0; r < ps->n_peers; ++r) {
+        if (!ps->peer_o[r] || !ps->peer_flags[r] || !ps->peer_ready[r])
+            return set_error(PLI_ERR_INVALID, "null peer pointer for rank %d", r);
+        peer.o[r] = ps->peer_o[r];
+        gather.done[r] = ps->peer_flags[r];
+        gather.ready[r] = ps->peer_ready[r];
+    }
+    peer.n = gather.n = ps->n_peers;
+    peer.epoch = gather.epoch = ps->epoch;
+    peer.buffer_stride = 0;
+    peer.slice_offset = ps->slice_offset;
+    // Publishing from the decode grid itself (its last CTA, found with a counter) needs a system-scope fence in EVERY CTA
+    // before it counts -- ~2.5 us during which the CTA keeps its SM slot; on a 1024-CTA grid that cost 27 us against 23 for
+    // the NCCL all-gather (2 GPUs, C5 ctx 1024).  The grid boundary is the cheaper fence: the one-warp publish / wait
+    // kernel is launched programmatically behind the decode grid (resident and waiting in griddepcontrol.wait when it
+    // ends), so a step is still one call and its second launch costs no launch latency.
+    gather.cta_counter = kPublishFromLastCta ? ps->cta_counter : nullptr;
+    gather.rank = ps->rank;
+    gather.timeout_ns = peer_timeout_ns();
+    gather.status = status_words();
+    if (num_splits == 0) num_splits = pli_decode_num_splits(B, Hkv, max_seq_len);
+    bool wrote_direct = false;
+    int rc = splitkv_impl(q, k_store, v_store, block_table, seq_lens, B, Hq, Hkv, D, max_seq_len, block_size, table_stride,
+                          layer, kv_extent, q_strides, kv_strides, scale, dtype, num_splits, workspace, workspace_bytes,
+                          static_cast<cudaStream_t>(stream), ps->peer_o[ps->rank], lse, o_strides, &wrote_direct, &peer,
+                          &gather);
+    if (rc) return rc;
+    if (!wrote_direct) return set_error(PLI_ERR_UNSUPPORTED, "internal: the gather launch did not take the fused path");
+    if (kPublishFromLastCta) return PLI_OK;
+    PeerFlags pf{};
+    for (int r = 0; r < ps->n_peers; ++r) pf.flags[r] = ps->peer_flags[r];
+    pf.n = ps->n_peers;
+    pf.rank = ps->rank;
+    pf.epoch = ps->epoch;
+    pf.timeout_ns = peer_timeout_ns();
+    pf.status = status_words();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, peer_publish_wait_kernel, pf));
+    count_launch();
+    return PLI_OK;
 }
 
 extern "C" int pli_peer_publish_wait(const pli_peer_scatter* ps, void* stream) {

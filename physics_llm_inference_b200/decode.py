@@ -158,14 +158,23 @@ def _prepare_decode(
             ps.peer_o[r] = peer_out.output_ptrs[r]
             ps.peer_flags[r] = peer_out.flag_ptrs[r]
         ps.epoch = peer_out.epoch_ptr
-        ps.buffer_stride = peer_out.buffer_stride
         ps.slice_offset = peer_out.slice_offset
+        # one launch and one buffer when the TMA kernel serves the call (pli_decode_fwd_gather), else two of each
+        st_i64 = _lib.i64(*kv_strides)
+        gather = scale > 0 and q3.stride(0) % 2 == 0 and q3.stride(1) % 2 == 0 and q3.data_ptr() % 4 == 0 and \
+            lib.pli_decode_kernel_kind(D, _lib.dtype_code(q3.dtype), bs, st_i64, k_cache.data_ptr(),
+                                       v_cache.data_ptr()) == _lib.PLI_KIND_MMA_TMA
+        peer_out.use_mode("gather" if gather else "scatter")
+        ps.buffer_stride = 0 if gather else peer_out.buffer_stride
+        for r in range(sh.world_size):
+            ps.peer_ready[r] = peer_out.ready_ptrs[r]
+        ps.cta_counter = peer_out.cta_counter_ptr
         ps_ref = ctypes.byref(ps)
         args = (q3.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), table_ptr, lens.data_ptr(), lse_ptr, B, Hq, Hkv, D,
                 max_seq_len, bs, tstride, layer, kv_extent, _lib.i64(q3.stride(0), q3.stride(1)), _lib.i64(*kv_strides),
                 _lib.i64(Ht * Dt, Dt), float(scale), _lib.dtype_code(q3.dtype), num_splits, workspace.data_ptr(), ws_bytes,
                 ps_ref)
-        return _Prepared(dev, True, args, keep + (ps,), None, lse, peer_out, ps, q.dim() == 4)
+        return _Prepared(dev, "gather" if gather else "scatter", args, keep + (ps,), None, lse, peer_out, ps, q.dim() == 4)
     if out is None:
         out = torch.empty((B, Hq, D), dtype=q.dtype, device=dev)
     elif out.shape != (B, Hq, D) or out.dtype != q.dtype or out.stride(-1) != 1:
@@ -174,7 +183,7 @@ def _prepare_decode(
             B, Hq, Hkv, D, max_seq_len, bs, tstride, layer, kv_extent, _lib.i64(q3.stride(0), q3.stride(1)),
             _lib.i64(*kv_strides), _lib.i64(out.stride(0), out.stride(1)), float(scale), _lib.dtype_code(q.dtype),
             num_splits, workspace.data_ptr(), ws_bytes)
-    return _Prepared(dev, False, args, keep, out, lse, None, None, q.dim() == 4)
+    return _Prepared(dev, "", args, keep, out, lse, None, None, q.dim() == 4)
 
 
 class _Prepared:
@@ -191,8 +200,11 @@ class _Prepared:
             stream = _lib.current_stream_ptr(self.dev)
             if self.scatter:
                 import ctypes
-                _lib.check(self.lib.pli_decode_fwd_scatter(*self.args, stream))
-                _lib.check(self.lib.pli_peer_publish_wait(ctypes.byref(self.ps), stream))
+                if self.scatter == "gather":
+                    _lib.check(self.lib.pli_decode_fwd_gather(*self.args, stream))
+                else:
+                    _lib.check(self.lib.pli_decode_fwd_scatter(*self.args, stream))
+                    _lib.check(self.lib.pli_peer_publish_wait(ctypes.byref(self.ps), stream))
                 # eager: the buffer of this step; under stream capture (nothing ran yet): the fixed `stable` tensor the
                 # captured step copies into — the caller accounts for replays with peer_out.advance(n)
                 o = self.peer_out.finish_step(self.ps, stream)

@@ -129,6 +129,7 @@ def flash_attention_forward(
         if len(peer_out.shape) != 4 or peer_out.dtype != q.dtype or \
                 (B, Hq, Nq, D) != (sh.b_end - sh.b_start, sh.q_end - sh.q_start, peer_out.shape[2], peer_out.shape[3]):
             raise RuntimeError(f"local q {tuple(q.shape)} / dtype does not match the PeerOutput shard {peer_out.shape}")
+        peer_out.use_mode("scatter")
         Bt, Ht, _, _ = peer_out.shape
         ps = _lib.PeerScatter()
         ps.n_peers, ps.rank = sh.world_size, sh.rank

@@ -110,10 +110,17 @@ class PeerOutput:
     would follow a head-sharded decode step is done by the kernel's own stores.
 
     The buffers live in torch symmetric memory (one allocation per rank, mapped into every process of the group):
-    [flag words, one per rank | step counter at byte 256 | pad to 512][buffer 0 (B, Hq, D)][buffer 1].
+    [done words, one per rank | ready words at byte 64 | step counter at byte 256, CTA counter at 260 | pad to 512]
+    [buffer 0 (B, Hq, D)][buffer 1].
     The step counter is read on the device, so the step can be captured in a CUDA graph; `epoch` mirrors it on
-    the host (call `advance()` after replaying a captured step).  Step e writes buffer e & 1, so a rank never
-    overwrites data a slower peer is still reading (see include/pli_attention.h)."""
+    the host (call `advance()` after replaying a captured step).
+
+    Two protocols (include/pli_attention.h), fixed by the first call that uses the object (`mode`):
+      "gather"   decode on the TMA kernel: ONE launch, ONE buffer (buffer 0, a fixed address: captures into a CUDA graph
+                 next to its consumers without a copy); a `ready` credit from every receiver replaces the second buffer,
+                 the last CTA of the grid publishes / waits for the `done` words (pli_decode_fwd_gather);
+      "scatter"  prefill, and decode on the SIMT kernel: step e writes buffer e & 1 so that a rank never overwrites data
+                 a slower peer is still reading, and a one-warp kernel publishes / waits behind the compute kernel."""
 
     def __init__(self, batch: int, num_heads: int, head_dim: int, dtype: torch.dtype, shard: HeadShard, *, group=None,
                  device=None, seq_len: int | None = None, graph_safe: bool = False):
@@ -154,7 +161,22 @@ class PeerOutput:
             self.handle = None
             self.base_ptrs = [self.storage.data_ptr()]
         self.epoch = 0                                        # host mirror of the device step counter
-        self.stable = torch.empty(self.shape, dtype=dtype, device=self.device) if graph_safe else None
+        self.mode = None                                      # "gather" | "scatter", see the class docstring
+        self.graph_safe = graph_safe
+        self._stable = None                                   # the fixed output of graph_safe "scatter" steps, on demand
+
+    @property
+    def stable(self):
+        if self._stable is None and self.graph_safe:
+            self._stable = torch.empty(self.shape, dtype=self.dtype, device=self.device)
+        return self._stable
+
+    def use_mode(self, mode: str) -> None:
+        if self.mode is None:
+            self.mode = mode
+        elif self.mode != mode:
+            raise RuntimeError(f"this PeerOutput has been used with the '{self.mode}' protocol; a '{mode}' step on the same "
+                               "object would mix one-buffer and two-buffer steps (use a second PeerOutput)")
 
     def finish_step(self, ps, stream: int) -> torch.Tensor:
         """Called by the fused entry points after pli_peer_publish_wait: the tensor the caller gets for this step."""
@@ -162,6 +184,8 @@ class PeerOutput:
         if not torch.cuda.is_current_stream_capturing():
             _lib.raise_on_device_fault()                      # e.g. a peer that never arrived in an EARLIER step
             return self.advance()
+        if self.mode == "gather":
+            return self.buffer(0)                             # one buffer, a fixed address: nothing to copy
         if self.stable is None:
             raise RuntimeError(
                 "a fused-gather step is being captured in a CUDA graph, but this PeerOutput has no fixed output: the "
@@ -181,7 +205,7 @@ class PeerOutput:
         """Account for `steps` steps launched on the device (a direct call does this itself; call it after replaying
         a CUDA graph that holds captured steps).  Returns the buffer of the latest step."""
         self.epoch += steps
-        return self.buffer(self.epoch & 1)
+        return self.buffer(0 if self.mode == "gather" else self.epoch & 1)
 
     @property
     def output_ptrs(self):
@@ -192,8 +216,16 @@ class PeerOutput:
         return list(self.base_ptrs)
 
     @property
+    def ready_ptrs(self):
+        return [p + 64 for p in self.base_ptrs]
+
+    @property
     def epoch_ptr(self) -> int:
         return self.base_ptrs[self.shard.rank] + 256
+
+    @property
+    def cta_counter_ptr(self) -> int:
+        return self.base_ptrs[self.shard.rank] + 260
 
     @property
     def buffer_stride(self) -> int:

@@ -270,12 +270,35 @@ def test_decode_peer_output_single_rank(splits):
     shard = pli.make_shard(0, 1, Hq, Hkv, B)
     po = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard)
     ref = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=splits)[:, :, 0]
+    launches = pli.launch_count()
     for step in range(3):
         o, lse = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=splits, peer_out=po,
                                   return_lse=True)
         assert o.shape == (B, Hq, D)
         assert torch.equal(o, ref), step
-    assert po.epoch == 3
+    assert po.epoch == 3 and po.mode == "gather"
+    assert pli.launch_count() - launches == 6, "decode (+ merge) kernel and the programmatically launched publish / wait"
+    # captured with a consumer in the same graph: one buffer at a fixed address, every replay is seen
+    ws = pli.decode_workspace(B, Hq, D, splits or pli.decode_num_splits(B, Hkv, L), "cuda")
+    consumed = torch.zeros(B, Hq, D, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=splits, peer_out=po, workspace=ws)
+        torch.cuda.synchronize()
+        with torch.cuda.graph(g):
+            og = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=splits, peer_out=po,
+                                  workspace=ws)
+            consumed.copy_(og.float() * 2)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        consumed.zero_()
+        g.replay()
+        o = po.advance()
+        torch.cuda.synchronize()
+        assert torch.equal(o, ref) and torch.equal(consumed, ref.float() * 2)
+    assert po.epoch == 7
 
 
 def test_decode_plan_matches_flash_decode_and_replays_in_a_graph():

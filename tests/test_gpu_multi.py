@@ -48,18 +48,14 @@ def _worker(rank, world, port, out_dir):
     kw = dict(block_tables=table, max_seq_len=max(lens_l))
     ref = pli.gather_heads(pli.flash_decode(qs, kps, vps, lens, **kw)[:, :, 0], shard)
     ws = pli.decode_workspace(qs.shape[0], qs.shape[1], D, pli.decode_num_splits(qs.shape[0], kps.shape[3], max(lens_l)), dev)
-    # ONE step per graph (an odd count: the double buffer a replay writes alternates), with a CONSUMER captured in the
-    # same graph (stands for o_proj / the next layer): it must see the step's output on every replay, which needs the
-    # fixed `stable` tensor of a graph_safe PeerOutput (the alternating buffer was returned here before)
-    try:
-        with torch.cuda.graph(torch.cuda.CUDAGraph()):
-            pli.flash_decode(qs, kps, vps, lens, peer_out=po, workspace=ws, **kw)
-        ok, why = False, "capturing a step of a PeerOutput without graph_safe=True did not raise"
-    except RuntimeError:
-        pass
+    # ONE step per graph with a CONSUMER captured in the same graph (stands for o_proj / the next layer): it must see the
+    # step's output on every replay.  The single-launch gather writes one buffer at a fixed address, so nothing special is
+    # needed (round 1 returned an alternating double buffer here; the two-buffer protocol still needs graph_safe).
     torch.cuda.synchronize()
     dist.barrier()
-    pog = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard, graph_safe=True)
+    if po.mode != "gather":
+        ok, why = False, f"the TMA decode path should use the single-launch gather, mode is {po.mode}"
+    pog = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard)
     consumed = torch.zeros(B, Hq, D, device=dev, dtype=torch.float32)
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))

@@ -39,7 +39,9 @@ def test_library_is_sm100a_native():
 
 def test_workspace_and_split_helpers_need_no_gpu():
     lib = _lib.load()
-    assert lib.pli_decode_workspace_bytes(64, 32, 128, 4) == 64 * 32 * 4 * 129 * 4
+    # partials (O and LSE, f32) + one 16-byte arrival-counter pair per (b, q head) upper bound, 8-byte aligned
+    assert lib.pli_decode_workspace_bytes(64, 32, 128, 4) == 64 * 32 * 4 * 129 * 4 + 64 * 32 * 16
+    assert lib.pli_decode_workspace_bytes(1, 1, 64, 1) == 264 + 16
     assert lib.pli_decode_workspace_bytes(0, 32, 128, 4) == 0
 
 
