@@ -275,6 +275,7 @@ struct DecodeTmaParams {
     void* o_final;                  // with osb / osh; unused when peer.n > 0
     float* lse_final;               // or NULL
     PeerGather gather;
+    int peer_vec;                   // the peers' slices can be written with 16-byte stores (alignment checked on the host)
 };
 
 // Arrival of one split's CTA on its unit's counter pair; returns the number of arrivals before this one.
@@ -359,10 +360,17 @@ __device__ __forceinline__ void combine_unit(const DecodeTmaParams& p, int b, in
         const int64_t off = b * p.osb + (h_base + row) * p.osh + dv;
         if (p.peer.n > 0) {
             const int64_t poff = p.peer.base() + off;
+            __align__(8) elem_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[e] = from_f32<elem_t>(ov[e]);
             for (int r = 0; r < p.peer.n; ++r) {
                 elem_t* dst = reinterpret_cast<elem_t*>(p.peer.o[r]) + poff;
+                if (p.peer_vec) {
+                    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(pk);
+                } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) dst[e] = from_f32<elem_t>(ov[e]);
+                    for (int e = 0; e < 4; ++e) dst[e] = pk[e];
+                }
             }
         } else {
             elem_t* dst = reinterpret_cast<elem_t*>(p.o_final) + off;
@@ -664,6 +672,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         // four elements per thread and pass, written as four independent chains (shared-memory reads, exp2, reciprocal,
         // store): one element at a time was ~600 dependent cycles per element and warp, 2400 of a short kernel's tail
         if (p.gather.n > 0 && p.o_direct != nullptr) mbar_wait(peer_ok, 0);      // the peers' buffers may be written
+        elem_t* stage_o = reinterpret_cast<elem_t*>(smem + 48 * 1024);           // [rows][kD], behind the merge area
         constexpr int kIlp = 4;
         for (int base = tid; base < rows_here * kD; base += kIlp * kConsumerWarps * 32) {
             float o_val[kIlp], lse_val[kIlp];
@@ -693,9 +702,13 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 if (idx >= rows_here * kD) break;
                 const int row = idx / kD, d = idx - row * kD;
                 if (p.o_direct != nullptr && p.peer.n > 0) {
-                    const int64_t off = p.peer.base() + b * p.osb + (h_base + row) * p.osh + d;
                     const elem_t val = from_f32<elem_t>(o_val[u]);
-                    for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[off] = val;
+                    if (p.peer_vec) {
+                        stage_o[idx] = val;                      // stored to the peers below, 16 bytes per thread
+                    } else {
+                        const int64_t off = p.peer.base() + b * p.osb + (h_base + row) * p.osh + d;
+                        for (int r = 0; r < p.peer.n; ++r) reinterpret_cast<elem_t*>(p.peer.o[r])[off] = val;
+                    }
                     if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val[u];
                 } else if (p.o_direct != nullptr) {
                     // single split: this CTA owns the whole sequence, so the combine pass is skipped
@@ -706,6 +719,18 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                     p.o_part[prow * kD + d] = o_val[u];
                     if (d == 0) p.lse_part[prow] = lse_val[u];
                 }
+            }
+        }
+        if (p.o_direct != nullptr && p.peer.n > 0 && p.peer_vec) {
+            // the slice goes to every rank over NVLink as 16-byte stores (512 contiguous bytes per warp instruction): a
+            // 2-byte store per thread and peer is an NVLink packet of 64 bytes per warp, mostly header
+            named_bar_sync(1, kConsumerWarps * 32);
+            const int64_t base_off = p.peer.base() + b * p.osb + h_base * p.osh;
+            for (int c = tid; c < rows_here * kD / 8; c += kConsumerWarps * 32) {
+                const int row = (c * 8) / kD, d = (c * 8) - row * kD;
+                const uint4 v = *reinterpret_cast<const uint4*>(stage_o + c * 8);
+                for (int r = 0; r < p.peer.n; ++r)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<elem_t*>(p.peer.o[r]) + base_off + row * p.osh + d) = v;
             }
         }
         if (threadIdx.x == 0) PLI_DECODE_TRACE(4);               // output / partial written
@@ -1093,6 +1118,13 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
         p.launch_id = next_launch_id();
         p.o_final = fused ? o_direct : nullptr;
         p.lse_final = fused ? lse_direct : nullptr;
+        p.peer_vec = 0;
+        if ((direct || fused) && peer != nullptr) {
+            bool ok = o_strides[0] % 8 == 0 && o_strides[1] % 8 == 0 && peer->slice_offset % 8 == 0 &&
+                      peer->buffer_stride % 8 == 0 && D % 8 == 0;
+            for (int r = 0; r < peer->n; ++r) ok = ok && (reinterpret_cast<uintptr_t>(peer->o[r]) & 15) == 0;
+            p.peer_vec = ok ? 1 : 0;
+        }
         p.gather = PeerGather{};
         if ((direct || fused) && peer != nullptr && gather != nullptr) p.gather = *gather;
         if (wrote_direct) *wrote_direct = direct || fused;
