@@ -454,6 +454,64 @@ def decode_c3(torch, pli, T, dev, rank, peaks, args):
                                  "runs only when num_splits > 1); algorithmic bytes = K,V once + q,o + table"}}
 
 
+def decode_cases(torch, pli, T, dev, peaks):
+    """Decode away from C3: the per-GPU share of C5 ctx 1024 on 8 GPUs (B256, 4q/1kv), one long sequence
+    (B1 x L32768) and a small batch (B8 x L8192), each as ONE launch (several splits are merged by the kernel itself),
+    eager through a DecodePlan and as a 12-step CUDA graph over rotating K/V pools (each step reads other HBM bytes)."""
+    rows = []
+    for name, B, Hq, Hkv, L in (("C5 ctx 1024, share of one of 8 GPUs", 256, 4, 1, 1024), ("one sequence, ctx 32768", 1, 32, 8, 32768),
+                                ("batch 8, ctx 8192", 8, 32, 8, 8192)):
+        D, bs = 128, 16
+        pages = B * L // bs
+        npools = 4
+        g = torch.Generator(device=dev).manual_seed(0xC0FFEE + 6)
+        pools = [(torch.empty(pages, 1, bs, Hkv, D, device=dev, dtype=torch.bfloat16).normal_(generator=g),
+                  torch.empty(pages, 1, bs, Hkv, D, device=dev, dtype=torch.bfloat16).normal_(generator=g)) for _ in range(npools)]
+        table = torch.randperm(pages, generator=torch.Generator().manual_seed(9)).to(torch.int32).view(B, L // bs).to(dev)
+        lens = torch.full((B,), L, dtype=torch.int32, device=dev)
+        q = torch.randn(B, Hq, 1, D, device=dev, generator=g).bfloat16()
+        S = pli.decode_num_splits(B, Hkv, L)
+        ws = pli.decode_workspace(B, Hq, D, S, dev)
+        out = torch.empty(B, Hq, D, device=dev, dtype=torch.bfloat16)
+        plans = [pli.DecodePlan(q, kp, vp, lens, block_tables=table, max_seq_len=L, num_splits=S, workspace=ws, out=out)
+                 for kp, vp in pools]
+
+        def eager():
+            for pl in plans:
+                pl()
+        pli.reset_launch_count()
+        eager()
+        launches = pli.launch_count() / npools
+        us_eager = T.timed(eager, 2, 10) * 1e3 / npools
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        steps = 12
+        with torch.cuda.stream(side):
+            eager()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(graph):
+                for i in range(steps):
+                    plans[i % npools]()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        us_graph = T.timed(graph.replay, 2, 10) * 1e3 / steps
+        nbytes = decode_bytes(B, Hq, Hkv, L, D, bs)
+        # CHECKER: the last step's output against the oracle on sequence 0
+        from oracle import attention_oracle as orc
+        kp, vp = pools[(steps - 1) % npools]
+        pg = table[0].long()
+        ro, _ = orc.cached_attention_oracle(q[0:1].cpu(), kp[pg, 0].reshape(1, L, Hkv, D).cpu(), vp[pg, 0].reshape(1, L, Hkv, D).cpu(), L)
+        err = (out[0:1].float().cpu().unsqueeze(2) - ro).abs().max().item()
+        rows.append({"workload": f"{name}: B{B} {Hq}q/{Hkv}kv D128 L{L}, 16-token pages", "num_splits": S,
+                     "launches_per_step": launches, "eager_us": us_eager, "graph_us": us_graph,
+                     "eager_gbs": nbytes / us_eager / 1e3, "graph_gbs": nbytes / us_graph / 1e3,
+                     "roofline": {"bound": "hbm", "achieved": nbytes / us_graph / 1e3, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": nbytes / us_graph / 1e3 / peaks["hbm_gbs"], "algorithmic_bytes": nbytes},
+                     "parity": {"oracle_max_abs_err": err, "tolerance": 2e-2, "ok": err <= 2e-2}})
+        del pools, plans
+    return rows
+
+
 def decode_c5_sweep(torch, pli, T, dev, rank, world):
     """BASELINE config 5: decode B256, paged, ctx sweep, KV heads sharded (8/W KV heads + their q heads per GPU).  With
     W > 1 the fused gather (one launch whose stores scatter O to every rank over NVLink + the flag wait) is timed against
@@ -845,6 +903,8 @@ def main():
     probe = h2d_probe(torch, T, dev, rank, world)
 
     decode = None if args.no_decode else decode_c3(torch, pli, T, dev, rank, peaks, args)
+    if decode is not None:
+        decode["cases"] = decode_cases(torch, pli, T, dev, peaks)
     shapes = None if args.no_shapes else prefill_shape_rows(torch, pli, T, dev, peaks)
     strong = None
     if not args.no_strong:

@@ -1836,9 +1836,21 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
     p.num_pairs = p.head_pairs ? (Nq + kBM - 1) / kBM : (Nq + 2 * kBM - 1) / (2 * kBM);
     const int64_t total = (int64_t)B * (p.head_pairs ? Hq / 2 : Hq) * p.num_pairs;
     p.total_items = total > 0x7fffffff ? -1 : (int)total;
-    // 4 when every CTA gets many items (the balance cost of a block amortises), else 2, never more than num_pairs
+    // Scheduling block (decode_item), in 128- or 256-row slots.  Inside a block the items are KV-group-major, so the larger
+    // the block, the fewer KV groups the ~148 items in flight touch and the more of the K/V re-reads stay in L2 (C2, ncu:
+    // 809 MB of DRAM reads with blocks of 8 slots, 593 with 16, 405 = the algorithmic 403 with one block of 64); but the
+    // schedule is longest-first only ACROSS blocks, and one block per launch costs 2 % in load balance.  So: the smallest
+    // power of two that gives every CTA ~12 items per block, at least the round-1 value (8 / 4 slots), at most half of
+    // the slots (two blocks).  C2: 32 slots, 1.05x the algorithmic DRAM traffic at an unchanged time.
     int grid = sm_count() > 0 ? sm_count() : 148;
-    p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);   // in 128- or 256-row slots
+    p.pair_block = (total >= (int64_t)16 * grid ? 4 : 2) * (p.head_pairs ? 2 : 1);
+    {
+        const int64_t per_slot = (int64_t)B * Hkv * (p.head_pairs ? group / 2 : group);
+        while ((int64_t)p.pair_block * per_slot < (int64_t)12 * grid && p.pair_block * 2 <= p.num_pairs / 2) p.pair_block *= 2;
+    }
+#ifdef PLI_PAIR_BLOCK
+    p.pair_block = PLI_PAIR_BLOCK;                                        // A/B builds: scheduling block in row slots
+#endif
     if (p.pair_block > p.num_pairs) p.pair_block = p.num_pairs;
     {
         const int gi = p.head_pairs ? group / 2 : group;                  // items per (KV group, slot)

@@ -18,14 +18,19 @@ def run(B, Hq, Hkv, N, D, causal, dtype=torch.bfloat16, reps=20):
     return pli.prefill_algorithmic_flops(B, Hq, N, N, D, causal) / (e0.elapsed_time(e1) / reps) / 1e9
 time.sleep(0.5)
 out = []
-out.append("C2 %%6.0f" %% run(4, 32, 8, 8192, 128, True))
-out.append("N2048 %%6.0f" %% run(16, 32, 8, 2048, 128, True))
-out.append("N512 %%6.0f" %% run(64, 32, 8, 512, 128, True))
-out.append("N128 %%6.0f" %% run(256, 32, 8, 128, 128, True))
-out.append("noncausal %%6.0f" %% run(4, 32, 8, 8192, 128, False, reps=10))
-out.append("fp16 %%6.0f" %% run(4, 32, 8, 8192, 128, True, torch.float16))
-out.append("D64 %%6.0f" %% run(4, 32, 8, 8192, 64, True))
-out.append("MHA %%6.0f" %% run(4, 32, 32, 8192, 128, True))
+only = os.environ.get("PLI_AB_ONLY", "").split(",") if os.environ.get("PLI_AB_ONLY") else None      # e.g. PLI_AB_ONLY=C2,D64
+def add(name, *a, **kw):
+    if only is None or name in only:
+        out.append(name + " %%6.0f" %% run(*a, **kw))
+add("C2", 4, 32, 8, 8192, 128, True)
+add("N2048", 16, 32, 8, 2048, 128, True)
+add("N512", 64, 32, 8, 512, 128, True)
+add("N128", 256, 32, 8, 128, 128, True)
+add("noncausal", 4, 32, 8, 8192, 128, False, reps=10)
+add("fp16", 4, 32, 8, 8192, 128, True, torch.float16)
+add("D64", 4, 32, 8, 8192, 64, True)
+add("D64nc", 4, 32, 8, 8192, 64, False, reps=10)
+add("MHA", 4, 32, 32, 8192, 128, True)
 print("  ".join(out))
 ''' % ROOT
 for rep in range(2):

@@ -1,4 +1,4 @@
-"""Short, fixed workloads for ncu captures (one GPU): `python tools/profile_target.py prefill|paged|decode [reps]`."""
+"""Short, fixed workloads for ncu captures (one GPU): `python tools/profile_target.py prefill|paged|decode|split [reps]`."""
 import os
 import sys
 
@@ -29,7 +29,8 @@ elif which == "paged":
     for _ in range(reps):
         pli.flash_attention_paged(q, kp, vp, table, lens, max_seq_len=N)
 else:
-    B, Hq, Hkv, D, L, bs = 64, 32, 8, 128, 4096, 16
+    # decode: C3, or ("split") one sequence of 32768 tokens = 37 splits per KV head merged by the kernel itself
+    B, Hq, Hkv, D, L, bs = (1, 32, 8, 128, 32768, 16) if which == "split" else (64, 32, 8, 128, 4096, 16)
     P = B * L // bs
     kp = torch.randn(P, 1, bs, Hkv, D, device="cuda").bfloat16()
     vp = torch.randn(P, 1, bs, Hkv, D, device="cuda").bfloat16()

@@ -19,6 +19,9 @@ if "c4" in d:
 if "decode" in d:
     x = d["decode"]
     print(f"decode C3: {x['value']:.0f} GB/s  {x['us_per_step']:.1f} us  frac {x['roofline']['frac']:.3f}  launches {x['gpu_launches']}")
+    for row in x.get("cases", []):
+        print(f"   {row['workload']:62s} splits {row['num_splits']:2d}  eager {row['eager_us']:6.1f} us {row['eager_gbs']:5.0f} GB/s  "
+              f"graph {row['graph_us']:6.1f} us {row['graph_gbs']:5.0f} GB/s  parity {row['parity']['ok']}")
     if "cpu_baseline" in x:
         print("   cpu:", r(x["cpu_baseline"]["value"]), x["cpu_baseline"]["unit"], x["cpu_baseline"]["cores"], "threads")
 for row in d.get("shapes", []):
