@@ -61,6 +61,9 @@ constexpr int kCorrCols = PLI_CORR_COLS;
 #ifndef PLI_SOFTMAX_PIPELINE
 #define PLI_SOFTMAX_PIPELINE 0
 #endif
+#ifndef PLI_SMEM_KEEP_SPACE
+#define PLI_SMEM_KEEP_SPACE 1
+#endif
 #ifndef PLI_DIRECT_EPILOGUE
 #define PLI_DIRECT_EPILOGUE 0
 #endif
@@ -311,7 +314,13 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     constexpr uint32_t kIdescO = make_idesc_f16(kMmaM, kD, kBf16, false, true);    // P V: B (V) is MN-major
 
     extern __shared__ uint8_t smem_raw[];
+#if PLI_SMEM_KEEP_SPACE
+    // an offset added to the __shared__ array (not a pointer rebuilt from an integer) keeps the address space: the scalar
+    // traffic through shared memory (scale factors, row statistics) compiles to LDS / STS instead of generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+#endif
     uint8_t* sQ = smem + L::kQOff;
     uint8_t* sKV = smem + L::kKVOff;
     uint8_t* sO = smem + L::kOOff;
@@ -1161,7 +1170,13 @@ prefill_wide_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     constexpr uint32_t kIdescO = make_idesc_f16(2 * kBM, kD, kBf16, false, true);     // P V
 
     extern __shared__ uint8_t smem_raw[];
+#if PLI_SMEM_KEEP_SPACE
+    // an offset added to the __shared__ array (not a pointer rebuilt from an integer) keeps the address space: the scalar
+    // traffic through shared memory (scale factors, row statistics) compiles to LDS / STS instead of generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+#endif
     uint8_t* sQ = smem + L::kQOff;
     uint8_t* sKV = smem + L::kKVOff;
     uint8_t* sO = smem + L::kOOff;
@@ -1615,7 +1630,13 @@ umma_selftest_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     constexpr uint32_t kIdescS = make_idesc_f16(128, 128, kBf16, false, false);
     constexpr uint32_t kIdescO = make_idesc_f16(128, kD, kBf16, false, true);
     extern __shared__ uint8_t smem_raw[];
+#if PLI_SMEM_KEEP_SPACE
+    // an offset added to the __shared__ array (not a pointer rebuilt from an integer) keeps the address space: the scalar
+    // traffic through shared memory (scale factors, row statistics) compiles to LDS / STS instead of generic LD / ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+#else
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+#endif
     uint8_t* sA = smem;
     uint8_t* sB = smem + kTileBytes;
     uint8_t* sC = smem + 2 * kTileBytes;
