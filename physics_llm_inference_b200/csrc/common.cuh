@@ -233,6 +233,15 @@ inline FastDiv make_fastdiv(uint32_t d) {
     return f;
 }
 
+// Plain (non-tensor) bulk copy global -> shared, completion on an mbarrier (bytes: a multiple of 16; both addresses
+// 16-byte aligned), and the proxy fence that orders generic-proxy accesses before async-proxy ones in all state spaces.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
     asm volatile("prefetch.global.L2 [%0];\n" ::"l"(ptr));
 }

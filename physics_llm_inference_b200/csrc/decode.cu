@@ -313,72 +313,113 @@ __device__ __forceinline__ void unit_reset(unsigned long long* c, uint32_t id, b
 }
 
 // Merge of the S partials of one unit (rows_here q heads of one sequence) by the 128 consumer threads of the CTA that
-// arrived last.  What this costs is the latency chain of the CTA that finishes last, so there is no shared memory and no
-// barrier in it: a thread owns four output columns of one row and walks ALL splits of that row itself, twenty at a time
-// (their LSEs -- the same addresses for the 32 lanes of a row, one transaction -- and 16-byte pieces of their outputs
-// requested together), merging batches with the running-maximum rule.  (A first version computed the weights per row in
-// one warp, spread (row, split) pairs over the threads and summed through shared memory: three barriers and three
-// dependent L2 round trips, 6100 cycles for S = 4 and 8700 for S = 37 against ~1700 for the arrival atomic itself.)
+// arrived last.  What this costs is the latency chain of the CTA that finishes last.  The unit's partial outputs are ONE
+// contiguous block of the workspace ([row][split][kD] f32: 76 KiB for 4 heads x 37 splits), so thread 0 pulls it into
+// the (idle) K/V ring with bulk copies -- one request instead of two to three rounds of twenty 16-byte loads per thread,
+// which is what the merge cost when it read the partials from L2 directly -- while every thread fetches the row's LSEs
+// and works out the weights; then a thread owns four output columns of one row and walks all splits in shared memory.
+// Units whose partials do not fit the ring are merged in groups of rows.  No other barrier, no shared-memory reduction.
+// (First version: weights per row in one warp, (row, split) pairs spread over the threads, sum through shared memory:
+// three barriers and three dependent L2 round trips, 6100 cycles for S = 4 and 8700 for S = 37 against ~1700 for the
+// arrival atomic itself.)
+// Thread 0 of the last arriver: bulk-copy rows [r0, r0 + nr) of the unit's partial outputs into shared memory.
+template <int kD>
+__device__ __forceinline__ void combine_fetch(const DecodeTmaParams& p, uint8_t* smem, uint64_t* bar, int b, int h_base, int r0,
+                                              int nr) {
+    // the partials were written through the generic proxy (by other CTAs, acquired by this thread's arrival); the bulk
+    // copy reads them, and overwrites shared memory this CTA has just read, through the async proxy
+    fence_proxy_async_all();
+    const uint32_t total = (uint32_t)(nr * p.S * kD * 4);
+    mbar_arrive_expect_tx(bar, total);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.o_part + ((int64_t)b * p.Hq + h_base + r0) * p.S * kD);
+    for (uint32_t off = 0; off < total; off += 32768u) bulk_load(smem + off, src + off, min(32768u, total - off), bar);
+}
+__device__ __forceinline__ int combine_rows_per_group(const DecodeTmaParams& p, int kD, int ring_bytes, int rows_here) {
+    return max(1, min(rows_here, ring_bytes / (p.S * kD * 4)));
+}
+
 template <int kD, typename elem_t>
-__device__ __forceinline__ void combine_unit(const DecodeTmaParams& p, int b, int h_base, int rows_here, int tid) {
+__device__ __forceinline__ void combine_unit(const DecodeTmaParams& p, uint8_t* smem, uint64_t* bar, int ring_bytes, int b,
+                                             int h_base, int rows_here, int tid) {
     const int S = p.S;
-    constexpr int kVec = kD / 4;                                  // float4 pieces per row
-    constexpr int kBatch = 20;                                    // 37 splits (one sequence on 296 CTA slots) in two rounds
-    for (int item = tid; item < rows_here * kVec; item += kConsumerWarps * 32) {
-        const int row = item / kVec, dv = (item % kVec) * 4;
-        const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * S;
-        const float* lp = p.lse_part + prow;
-        const float* op = p.o_part + prow * kD + dv;
-        float M = -INFINITY, den = 0.f;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s0 = 0; s0 < S; s0 += kBatch) {
-            float l[kBatch];
-            float4 v[kBatch];
+    constexpr int kVec = kD / 4;                                  // lanes per row: 32 (D 128) or 16 (D 64), 16 bytes each
+    constexpr int kPerLane = 64 / kVec;                           // LSEs per lane (S <= 64)
+    const int lane_in_row = tid % kVec;
+    const int row_bytes = S * kD * 4;
+    const int rows_per_group = combine_rows_per_group(p, kD, ring_bytes, rows_here);
+    float* stage = reinterpret_cast<float*>(smem);                // [rows of the group][S][kD]
+    uint32_t parity = 0;
+    for (int r0 = 0; r0 < rows_here; r0 += rows_per_group) {
+        const int nr = min(rows_per_group, rows_here - r0);
+        if (r0 > 0) named_bar_sync(1, kConsumerWarps * 32);       // the previous group has been read
+        if (tid == 0 && r0 > 0) combine_fetch<kD>(p, smem, bar, b, h_base, r0, nr);    // (group 0: requested by the caller)
+        const int n_items = nr * kVec;
+        for (int base = (tid / 32) * 32; base < n_items; base += kConsumerWarps * 32) {      // warp-uniform trip count
+            const int item = base + (tid % 32);
+            const bool live = item < n_items;
+            const int row = r0 + min(item, n_items - 1) / kVec, dv = lane_in_row * 4;
+            const float* lp = p.lse_part + ((int64_t)b * p.Hq + h_base + row) * S;
+            // the row's weights, spread over its kVec lanes
+            float l[kPerLane], w[kPerLane];
+            float M = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const int sp = s0 + j;
-                l[j] = sp < S ? __ldcg(lp + sp) : -INFINITY;
-                v[j] = sp < S ? __ldcg(reinterpret_cast<const float4*>(op + (int64_t)sp * kD)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < kPerLane; ++k) {
+                const int si = lane_in_row + k * kVec;
+                l[k] = si < S ? __ldcg(lp + si) : -INFINITY;
+                M = fmaxf(M, l[k]);
             }
-            float bm = M;
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) bm = fmaxf(bm, l[j]);
-            const float sc = M == -INFINITY ? 0.f : __expf(M - bm);
-            den *= sc;
-            acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+            for (int o2 = kVec / 2; o2 > 0; o2 >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o2));
+            float den = 0.f;
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) {
-                const float w = l[j] == -INFINITY ? 0.f : __expf(l[j] - bm);
-                den += w;
-                acc.x = fmaf(w, v[j].x, acc.x); acc.y = fmaf(w, v[j].y, acc.y);
-                acc.z = fmaf(w, v[j].z, acc.z); acc.w = fmaf(w, v[j].w, acc.w);
+            for (int k = 0; k < kPerLane; ++k) {
+                w[k] = l[k] == -INFINITY ? 0.f : __expf(l[k] - M);
+                den += w[k];
             }
-            M = bm;
-        }
-        const float inv = den > 0.f ? 1.f / den : 0.f;
-        const float ov[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
-        const int64_t off = b * p.osb + (h_base + row) * p.osh + dv;
-        if (p.peer.n > 0) {
-            const int64_t poff = p.peer.base() + off;
-            __align__(8) elem_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pk[e] = from_f32<elem_t>(ov[e]);
-            for (int r = 0; r < p.peer.n; ++r) {
-                elem_t* dst = reinterpret_cast<elem_t*>(p.peer.o[r]) + poff;
-                if (p.peer_vec) {
-                    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(pk);
-                } else {
+            for (int o2 = kVec / 2; o2 > 0; o2 >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o2);
+            const float inv = den > 0.f ? 1.f / den : 0.f;
+            mbar_wait(bar, parity);                               // the group's partial outputs are in shared memory
+            const float* sp = stage + (size_t)(row - r0) * S * kD + dv;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) dst[e] = pk[e];
+            for (int k = 0; k < kPerLane; ++k) {
+                if (k * kVec >= S) break;                         // warp-uniform
+                const int nj = min(kVec, S - k * kVec);
+#pragma unroll 4
+                for (int j = 0; j < nj; ++j) {
+                    const float wj = __shfl_sync(0xffffffffu, w[k], j, kVec);
+                    const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)(k * kVec + j) * kD);
+                    acc.x = fmaf(wj, v.x, acc.x); acc.y = fmaf(wj, v.y, acc.y);
+                    acc.z = fmaf(wj, v.z, acc.z); acc.w = fmaf(wj, v.w, acc.w);
                 }
             }
-        } else {
-            elem_t* dst = reinterpret_cast<elem_t*>(p.o_final) + off;
+            if (!live) continue;
+            const float ov[4] = {acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv};
+            const int64_t off = b * p.osb + (h_base + row) * p.osh + dv;
+            if (p.peer.n > 0) {
+                const int64_t poff = p.peer.base() + off;
+                __align__(8) elem_t pk[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) dst[e] = from_f32<elem_t>(ov[e]);
+                for (int e = 0; e < 4; ++e) pk[e] = from_f32<elem_t>(ov[e]);
+                for (int r = 0; r < p.peer.n; ++r) {
+                    elem_t* dst = reinterpret_cast<elem_t*>(p.peer.o[r]) + poff;
+                    if (p.peer_vec) {
+                        *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(pk);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) dst[e] = pk[e];
+                    }
+                }
+            } else {
+                elem_t* dst = reinterpret_cast<elem_t*>(p.o_final) + off;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dst[e] = from_f32<elem_t>(ov[e]);
+            }
+            if (dv == 0 && p.lse_final != nullptr)
+                p.lse_final[(int64_t)b * p.Hq + h_base + row] = den > 0.f ? M + logf(den) : -INFINITY;
         }
-        if (dv == 0 && p.lse_final != nullptr)
-            p.lse_final[(int64_t)b * p.Hq + h_base + row] = den > 0.f ? M + logf(den) : -INFINITY;
+        parity ^= 1u;
     }
 }
 
@@ -402,6 +443,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(v_tiles + kDecodeStages * kTileBytes);
     uint64_t* empty_bar = full_bar + kDecodeStages;
     uint64_t* peer_ok = empty_bar + kDecodeStages + 1;        // (empty_bar[kDecodeStages] is the is_last word)
+    uint64_t* merge_bar = peer_ok + 1;                        // the last arriver's bulk copy of the unit's partials
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x, b = blockIdx.z;
@@ -459,6 +501,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             mbar_init(&empty_bar[i], kConsumerWarps);
         }
         mbar_init(peer_ok, 1);
+        mbar_init(merge_bar, 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -737,16 +780,25 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         if (p.counters != nullptr) {
             // ---- fused combine: the last split of this unit to arrive merges all of them ----
             // (the partial stores of all 128 threads happen before thread 0's release through the CTA barrier; the merge
-            // reads the partials with ld.global.cg, i.e. from L2, after the barrier that follows thread 0's acquire)
+            // reads the partial outputs through thread 0's bulk copy, issued behind its acquire and a proxy fence, and
+            // the partial LSEs with ld.global.cg, i.e. from L2, after the barrier that follows the acquire)
             int* is_last = reinterpret_cast<int*>(empty_bar + kDecodeStages);
             named_bar_sync(1, kConsumerWarps * 32);
             unsigned long long* ctr = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);
             bool tagged = false;
-            if (tid == 0) *is_last = unit_arrive(ctr, p.launch_id, tagged) == (uint32_t)p.S - 1u;
+            if (tid == 0) {
+                const bool last = unit_arrive(ctr, p.launch_id, tagged) == (uint32_t)p.S - 1u;
+                *is_last = last;
+                // (every consumer thread is past its last read of the merge area: the barrier above) the first group of the
+                // unit's partials is requested before the other threads even learn that this CTA merges
+                if (last)
+                    combine_fetch<kD>(p, smem, merge_bar, b, h_base, 0,
+                                      min(rows_here, combine_rows_per_group(p, kD, 2 * kDecodeStages * kTileBytes, rows_here)));
+            }
             named_bar_sync(1, kConsumerWarps * 32);
             if (*is_last) {
                 if (p.gather.n > 0) mbar_wait(peer_ok, 0);
-                combine_unit<kD, elem_t>(p, b, h_base, rows_here, tid);
+                combine_unit<kD, elem_t>(p, smem, merge_bar, 2 * kDecodeStages * kTileBytes, b, h_base, rows_here, tid);
                 if (tid == 0) unit_reset(ctr, p.launch_id, tagged);
                 if (threadIdx.x == 0) PLI_DECODE_TRACE(5);       // combined output written
             }
@@ -967,7 +1019,7 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
     auto kern = decode_tma_kernel<kD, kBf16, kRows16>;
     constexpr int kTileBytes = (kD / 64) * kStageTokens * 128;
     const size_t merge_bytes = (size_t)(128 + 64 * (kD + 8)) * sizeof(float);
-    size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 16 + 1024;
+    size_t smem = (size_t)2 * kDecodeStages * kTileBytes + 2 * kDecodeStages * sizeof(uint64_t) + 24 + 1024;
     if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, (int)smem));
     PLI_CUDA_CHECK(bind_status_symbol());

@@ -61,6 +61,9 @@ constexpr int kCorrCols = PLI_CORR_COLS;
 #ifndef PLI_SOFTMAX_PIPELINE
 #define PLI_SOFTMAX_PIPELINE 0
 #endif
+#ifndef PLI_TILE1_DELAY
+#define PLI_TILE1_DELAY 0
+#endif
 #ifndef PLI_SMEM_KEEP_SPACE
 #define PLI_SMEM_KEEP_SPACE 1
 #endif
@@ -614,6 +617,15 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (; s < nt; ++s) half_step(s, std::false_type{});
 #else
             for (int s = 0; s < nt; ++s) {
+#if PLI_TILE1_DELAY > 0
+                // A/B option: put the two Q tiles' softmax warpgroups in ANTI-phase.  Left alone they run in phase (both
+                // start when Q and the first K tile land), so their exponentials and the correction warps' share collide on
+                // the one MUFU pipe of each scheduler and are idle together in the load / max phases.
+                if (t == 1 && s == 1 && nt > 8) {
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < PLI_TILE1_DELAY) __nanosleep(64);
+                }
+#endif
                 if (s >= 1 && s < n_plain) half_step(s, std::true_type{});
                 else half_step(s, std::false_type{});
             }

@@ -11,7 +11,9 @@ __global__ void k(int mode, int iters, float* out, long long* cyc) {
         for (int i = 0; i < 16; ++i) {
             if (mode == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[i]));
             else if (mode == 1) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(x[i]));
-            else asm volatile("{.reg .b64 a; mov.b64 a, {%0, %1}; fma.rn.f32x2 a, a, a, a; mov.b64 {%0, %1}, a;}" : "+f"(x[i]), "+f"(x[(i + 1) & 15]));
+            else if (mode == 2) asm volatile("{.reg .b64 a; mov.b64 a, {%0, %1}; fma.rn.f32x2 a, a, a, a; mov.b64 {%0, %1}, a;}" : "+f"(x[i]), "+f"(x[(i + 1) & 15]));
+            else if (mode == 3) asm volatile("{.reg .b32 a; mov.b32 a, %0; ex2.approx.ftz.bf16x2 a, a; mov.b32 %0, a;}" : "+f"(x[i]));   // two bf16 results per op
+            else asm volatile("{.reg .b32 a; mov.b32 a, %0; ex2.approx.f16x2 a, a; mov.b32 %0, a;}" : "+f"(x[i]));
         }
     }
     long long t1 = clock64();
@@ -23,8 +25,8 @@ __global__ void k(int mode, int iters, float* out, long long* cyc) {
 int main() {
     float* out; long long* cyc;
     cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 8);
-    const char* names[] = {"MUFU.EX2", "FFMA", "FFMA2"};
-    for (int mode = 0; mode < 3; ++mode)
+    const char* names[] = {"MUFU.EX2", "FFMA", "FFMA2", "EX2.bf16x2", "EX2.f16x2"};
+    for (int mode = 0; mode < 5; ++mode)
         for (int warps = 4; warps <= 16; warps *= 2) {      // warps per CTA = warps per SM; 4 schedulers
             k<<<148, warps * 32>>>(mode, 1000, out, cyc); cudaDeviceSynchronize();
             k<<<148, warps * 32>>>(mode, 1000, out, cyc); cudaDeviceSynchronize();
