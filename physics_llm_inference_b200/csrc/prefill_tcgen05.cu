@@ -61,6 +61,12 @@ constexpr int kCorrCols = PLI_CORR_COLS;
 #ifndef PLI_SOFTMAX_PIPELINE
 #define PLI_SOFTMAX_PIPELINE 0
 #endif
+// Columns of a hot half-step whose exponentials are issued before the step's row maximum is known (see half_step).
+#ifndef PLI_SPEC_COLS
+#define PLI_SPEC_COLS 0
+#endif
+constexpr int kSpecCols = PLI_SPEC_COLS;
+static_assert(kSpecCols == 0 || kSpecCols == 8 || kSpecCols == 16 || kSpecCols == 24, "kSpecCols: 0, 8, 16 or 24");
 #ifndef PLI_TILE1_DELAY
 #define PLI_TILE1_DELAY 0
 #endif
@@ -451,6 +457,16 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         for (int i = 0; i < 64; ++i) sv[i] = (i <= vis) ? sv[i] : -INFINITY;
                     }
                 }
+                // Speculative start (hot instance): the first kSpecCols exponentials are issued against the reference maximum the
+                // row ALREADY has, before the maximum of this half-step is known -- it changes the reference only when it
+                // exceeds it by more than the lazy-rescale threshold (rare after the first steps; the cold branch below then
+                // recomputes those columns).  The MUFU work overlaps the serial max / post prefix of the step.
+                [[maybe_unused]] uint32_t spk[kSpecCols > 0 ? kSpecCols / 2 : 1];
+                [[maybe_unused]] float2 sacc0 = make_float2(0.f, 0.f), sacc1 = make_float2(0.f, 0.f);
+                if constexpr (kInterior && kSpecCols > 0) {
+                    const float nmc_old = m_ref == -INFINITY ? 0.f : -m_ref * c;
+                    exp_cols<kBf16, kSpecCols>(sv, make_float2(c, c), make_float2(nmc_old, nmc_old), sacc0, sacc1, spk);
+                }
                 float mx0 = sv[0], mx1 = sv[1], mx2 = sv[2], mx3 = sv[3];
 #pragma unroll
                 for (int i = 4; i < 64; i += 4) {
@@ -461,12 +477,14 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
                 float alpha = 1.f;
+                [[maybe_unused]] bool spec_ok = kInterior && kSpecCols > 0;
                 if (!kInterior && s == 0) {
                     m_ref = m_new;                        // first half-step: nothing accumulated yet
                 } else if ((m_new - m_ref) * c > kRescaleThreshold) {
                     alpha = ex2_approx((m_ref - m_new) * c);
                     m_ref = m_new;
                     d *= alpha;
+                    spec_ok = false;
                 }
                 // a row that has seen no visible key yet (seq_len < its query's position: a caller error the kernel
                 // survives) keeps m_ref = -inf: exponentiate against 0 so that P = 0 instead of NaN
@@ -486,7 +504,19 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 constexpr int kSoft = kHN - kCorrCols;                // this warp's columns of a step s >= 1
                 {
                     uint32_t pk[16];
-                    exp_cols<kBf16, 32>(sv, c2, nmc2, acc0, acc1, pk);
+                    if constexpr (kInterior && kSpecCols > 0) {
+                        if (spec_ok) {
+#pragma unroll
+                            for (int i = 0; i < kSpecCols / 2; ++i) pk[i] = spk[i];
+                            acc0 = sacc0;
+                            acc1 = sacc1;
+                        } else {
+                            exp_cols<kBf16, kSpecCols>(sv, c2, nmc2, acc0, acc1, pk);
+                        }
+                        exp_cols<kBf16, 32 - kSpecCols>(sv + kSpecCols, c2, nmc2, acc0, acc1, pk + kSpecCols / 2);
+                    } else {
+                        exp_cols<kBf16, 32>(sv, c2, nmc2, acc0, acc1, pk);
+                    }
                     tmem_st_x16(s_addr, pk);
                 }
                 if constexpr (kSoft > 32) {
