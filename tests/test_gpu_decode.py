@@ -402,3 +402,28 @@ def test_fused_combine_matches_the_two_pass_path_on_a_dirty_workspace(B, G, D, L
         g.replay()
         torch.cuda.synchronize()
         assert torch.equal(out, first)
+
+
+def test_peer_output_on_the_simt_path_keeps_the_two_buffer_protocol():
+    """f32 storage is served by the SIMT split-KV kernel + the combine kernel: the gather then runs the round-1 protocol
+    (two buffers by step parity, publish / wait kernel behind the compute kernels) and the PeerOutput records that; mixing
+    it with a single-buffer step on the same object is refused."""
+    B, Hq, Hkv, D, bs, L = 4, 4, 2, 64, 16, 300
+    q, kp, vp, table, lens = orc.seeded_paged(33, B, Hq, Hkv, D, bs, [L] * B, dtype=torch.float32)
+    q, kp, vp, table, lens = q.cuda(), kp.cuda(), vp.cuda(), table.cuda(), lens.cuda()
+    shard = pli.make_shard(0, 1, Hq, Hkv, B)
+    po = pli.PeerOutput(B, Hq, D, torch.float32, shard)
+    ref = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L)[:, :, 0]
+    for step in range(3):
+        o = pli.flash_decode(q, kp, vp, lens, block_tables=table, max_seq_len=L, peer_out=po)
+        assert torch.equal(o, ref), step
+        assert o.data_ptr() == po.buffer((step + 1) & 1).data_ptr()
+    assert po.mode == "scatter" and po.epoch == 3
+    ro, _ = orc.paged_decode_oracle(q, kp, vp, table, lens)
+    assert (ref.cpu().unsqueeze(2) - ro).abs().max().item() <= 1e-3
+    pob = pli.PeerOutput(B, Hq, D, torch.bfloat16, shard)
+    qb, kb, vb = q.bfloat16(), kp.bfloat16(), vp.bfloat16()
+    pli.flash_decode(qb, kb, vb, lens, block_tables=table, max_seq_len=L, peer_out=pob)
+    assert pob.mode == "gather"
+    with pytest.raises(RuntimeError, match="protocol"):
+        pob.use_mode("scatter")
