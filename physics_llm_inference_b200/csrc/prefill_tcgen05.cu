@@ -67,6 +67,15 @@ constexpr int kCorrCols = PLI_CORR_COLS;
 #endif
 constexpr int kSpecCols = PLI_SPEC_COLS;
 static_assert(kSpecCols == 0 || kSpecCols == 8 || kSpecCols == 16 || kSpecCols == 24, "kSpecCols: 0, 8, 16 or 24");
+// Option (off): epilogue without CTA-wide barriers -- every correction warp converts its own 32 rows in 32-column chunks
+// into a private, double-buffered 2 KiB staging slot and issues its own TMA stores (32 x 32 boxes, 64-byte swizzle).
+// Correct (all parity tests), not faster: N 512 547-556 against 561-564 TFLOP/s, N 128 202-204 against 209-210, C2 equal
+// (profiles/r02_ab_warp_epilogue.log).  The in-kernel timeline shows why: the 2200-2900 cycles between "epilogue start" and
+// "epilogue done" of a tile are mostly the wait for the item's last PV to complete, not the conversion and the stores.
+// Default: the round-1 epilogue (a 64-column half of the tile at a time through one 16 KiB buffer).
+#ifndef PLI_WARP_EPILOGUE
+#define PLI_WARP_EPILOGUE 0
+#endif
 #ifndef PLI_TILE1_DELAY
 #define PLI_TILE1_DELAY 0
 #endif
@@ -163,8 +172,11 @@ struct PrefillParams {
 // transfer rides behind the MMAs of the following tiles.  n == 0: plain local store through map_o.
 struct PeerMaps {
     CUtensorMap maps[2][PLI_MAX_PEERS];   // [buffer][rank]: 4-D maps over the full output of that rank
+    // the local output once more with 32-column x 32-row boxes (64-byte swizzle): the per-warp epilogue stores
+    CUtensorMap o32;
     const uint32_t* epoch;
     int n, head_offset, batch_offset;
+    int warp_store;                       // o32 is valid: n == 0 and the output is the caller's own tensor
 };
 
 // CTA 0 timeline: each tracing warp owns region `region` of the buffer and keeps its own cursor in a
@@ -782,8 +794,48 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // a warp's 16-byte stores to 32 different rows cost more than the barriers they save; the per-tile epilogue
                 // went from ~2500 to ~3500 cycles and N = 512 from 560 to 500 TFLOP/s.  -DPLI_DIRECT_EPILOGUE=1 rebuilds it.)
                 if (kDirectEpilogue && p.o_base != nullptr && peers.n == 0) direct = true;
+                const bool warp_store = PLI_WARP_EPILOGUE && peers.warp_store && !direct;
+                if (warp_store) {
+                    // ---- per-warp epilogue: this warp's 32 rows, 32 columns at a time, two private 2 KiB slots ----
+                    // (the round-1 epilogue below costs ~2400 cycles per tile: per 64-column half it waits for the previous
+                    // TMA store to release the one staging buffer and crosses two 128-thread barriers; a short item pays
+                    // that twice, one tile after the other, in front of the next item's first PV)
+                    uint8_t* wbuf = sO + wq * 4096;
 #pragma unroll
-                for (int hf = 0; hf < kHalves; ++hf) {
+                    for (int ch = 0; ch < kD / 32; ++ch) {
+                        uint8_t* buf = wbuf + (ch & 1) * 2048;
+                        if (lane == 0) tma_store_wait_read<1>();      // the store that read this slot two chunks ago is done
+                        __syncwarp();
+                        float orr[32];
+                        tmem_ld_x32(tmem_base + 256 + t * 128 + lane_addr + ch * 32, orr);
+                        tc_wait_ld();
+                        if (ch == kD / 32 - 1) {
+                            tc_fence_before();
+                            __syncwarp();
+                            // O_t is in registers: the next item's PV_t(0) (buffer 0) may overwrite it
+                            if (lane == 0) arrive_pv_ok(t * 2);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 val;
+                            val.x = pack2<kBf16>(orr[8 * i + 0] * inv, orr[8 * i + 1] * inv);
+                            val.y = pack2<kBf16>(orr[8 * i + 2] * inv, orr[8 * i + 3] * inv);
+                            val.z = pack2<kBf16>(orr[8 * i + 4] * inv, orr[8 * i + 5] * inv);
+                            val.w = pack2<kBf16>(orr[8 * i + 6] * inv, orr[8 * i + 7] * inv);
+                            // 64-byte rows, 64-byte swizzle: 16-byte chunk i of row r sits at chunk i ^ ((r >> 1) & 3)
+                            *reinterpret_cast<uint4*>(buf + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = val;
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (q_tile0 + wq * 32 < it.nq)
+                                tma_store_4d_hint(&peers.o32, buf, ch * 32, it.qbase + q_tile0 + wq * 32, it.h[t], it.bq, kHintO);
+                            tma_store_commit();                       // (an empty group keeps the slot accounting uniform)
+                        }
+                    }
+                }
+#pragma unroll
+                for (int hf = 0; hf < (warp_store ? 0 : kHalves); ++hf) {
                     // the previous TMA store must have finished reading sO before it is overwritten
                     if (!direct) {
                         if (warp == 8 && lane == 0) tma_store_wait_read<0>();
@@ -843,7 +895,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 sf_base ^= (uint32_t)((it.n[t] >> 1) & 1) << (t * 2 + 1);
             }
         }
-        if (warp == 8 && lane == 0) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_all<0>();           // every correction warp's own stores (warp 8's in the staged form)
     } else {
         reg_dealloc<64>();
         if ((warp == 12 || warp == 13) && !(kPairMma && cta_rank != 0)) {
@@ -1784,7 +1836,7 @@ int g_debug_flags = 0;
 #endif
 
 int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int H, int B, const int64_t* st,
-                int box_rows = 128) {
+                int box_rows = 128, int box_cols = 64) {
     EncodeTiledFn enc = get_encode_tiled();
     if (enc == nullptr) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     const CUtensorMapDataType dt = dtype == PLI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -1798,10 +1850,11 @@ int make_map_4d(CUtensorMap* map, const void* base, int dtype, int D, int N, int
                              (long long)st[i], sizes[i]);
     auto fix = [&](int64_t s) -> cuuint64_t { return (cuuint64_t)(s > 0 ? s : (int64_t)D) * 2; };
     cuuint64_t strides[3] = {fix(st[2]), fix(st[1]), fix(st[0])};
-    cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, dt, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(PLI_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return PLI_OK;
 }
@@ -1964,6 +2017,9 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
     if ((rc = make_pool_map(&mk, k_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
     if ((rc = make_pool_map(&mv, v_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
     if ((rc = make_map_4d(&mo, o, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, os))) return rc;
+    PeerMaps pm = no_peers();
+    if ((rc = make_map_4d(&pm.o32, o, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, os, 32, 32))) return rc;
+    pm.warp_store = 1;
     PrefillParams p;
     p.lse = lse;
     p.B = B;
@@ -1994,7 +2050,7 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
     }
     const bool bf16 = dtype == PLI_BF16;
 #define PLI_GO(DD, BF)                                                                                  \
-    return pairs ? launch_t<DD, BF, 2, true>(mq, mk, mv, mo, p, stream) : launch_t<DD, BF, 1, true>(mq, mk, mv, mo, p, stream)
+    return pairs ? launch_t<DD, BF, 2, true>(mq, mk, mv, mo, p, stream, pm) : launch_t<DD, BF, 1, true>(mq, mk, mv, mo, p, stream, pm)
     if (D == 128) {
         if (bf16) PLI_GO(128, true);
         PLI_GO(128, false);
@@ -2073,6 +2129,10 @@ int launch_prefill_tcgen05(const void* q, const void* k, const void* v, void* o,
     if ((rc = make_map_4d(&mv, v, dtype, D, Nk, Hkv, B, vs, pair_mma ? kBN : pairs ? kHN : kBN))) return rc;
     if (peer != nullptr) mo = pm.maps[0][0];
     else if ((rc = make_map_4d(&mo, o, dtype, D, Nq, Hq, B, os))) return rc;
+    if (peer == nullptr) {
+        if ((rc = make_map_4d(&pm.o32, o, dtype, D, Nq, Hq, B, os, 32, 32))) return rc;
+        pm.warp_store = 1;
+    }
     PrefillParams p;
     p.lse = lse;
     p.B = B;
