@@ -338,7 +338,8 @@ def test_decode_plan_matches_flash_decode_and_replays_in_a_graph():
 
 
 @pytest.mark.parametrize("B,G,D,L,splits", [(1, 4, 128, 32768, 37), (3, 8, 64, 5000, 64), (2, 16, 128, 2000, 5),
-                                            (4, 32, 128, 777, 3)])
+                                            (4, 32, 128, 777, 3),
+                                            (2, 16, 128, 4500, 64)])     # 16 rows x 64 splits x 512 B: merged in three groups
 def test_fused_combine_matches_the_two_pass_path_on_a_dirty_workspace(B, G, D, L, splits):
     """Several splits per sequence: the split-KV kernel's last-arriving CTA of every unit merges the partials itself (no
     combine launch).  Its arrival counters live in the caller's workspace and need no initialisation: the same answer
