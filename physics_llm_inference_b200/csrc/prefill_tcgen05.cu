@@ -73,6 +73,12 @@ static_assert(kSpecCols == 0 || kSpecCols == 8 || kSpecCols == 16 || kSpecCols =
 // (profiles/r02_ab_warp_epilogue.log).  The in-kernel timeline shows why: the 2200-2900 cycles between "epilogue start" and
 // "epilogue done" of a tile are mostly the wait for the item's last PV to complete, not the conversion and the stores.
 // Default: the round-1 epilogue (a 64-column half of the tile at a time through one 16 KiB buffer).
+#ifndef PLI_LD64
+#define PLI_LD64 0                     // the softmax warps read a half-step's 64 scores with one tcgen05.ld.x64 instead of two x32
+#endif
+#ifndef PLI_CORR_SUSPEND_NS
+#define PLI_CORR_SUSPEND_NS 1000       // suspend-time hint of the correction warps' wait for the posted scale factor
+#endif
 #ifndef PLI_WARP_EPILOGUE
 #define PLI_WARP_EPILOGUE 0
 #endif
@@ -454,8 +460,12 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 tc_fence_after();
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 1, t, s);       // S ready
                 float sv[64];
+#if PLI_LD64
+                tmem_ld_x64(s_addr, sv);
+#else
                 tmem_ld_x32(s_addr + 0, sv + 0);
                 tmem_ld_x32(s_addr + 32, sv + 32);
+#endif
                 tc_wait_ld();
                 if ((warp & 3) == 0) trace_event(p, lane, t, trace_cur, 6, t, s);       // S in registers
                 if constexpr (!kInterior) {
@@ -716,7 +726,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #if defined(PLI_CORR_SPIN) && PLI_CORR_SPIN
                     mbar_wait(&sc_full[bi], (sc_par >> bi) & 1);
 #else
-                    mbar_wait_relaxed(&sc_full[bi], (sc_par >> bi) & 1);
+                    mbar_wait_relaxed<PLI_CORR_SUSPEND_NS>(&sc_full[bi], (sc_par >> bi) & 1);
 #endif
                     sc_par ^= 1u << bi;
                     if (wq == 0) trace_event(p, lane, 4, trace_cur, 8, t, s);             // scale factor seen
