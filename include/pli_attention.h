@@ -142,7 +142,8 @@ int pli_prefill_kernel_kind(int D, int dtype, const int64_t q_strides[3], const 
  *   num_splits  = KV splits per (b, kv head), 1..64; pass 0 to let the library pick
  *                 (pli_decode_num_splits); workspace must hold pli_decode_workspace_bytes() and
  *                 needs NO initialisation (it carries the partials and, behind them, one arrival
- *                 counter pair per (b, kv head) that tolerates any previous contents).
+ *                 counter pair per (b, kv head) that tolerates any previous contents); 16-byte
+ *                 aligned; launches that share one must be ordered (e.g. issued on one stream).
  *
  * pli_decode_fwd is ONE launch on the TMA path (bf16 / f16, head_dim 64 / 128): with several splits the
  * CTA of a (b, kv head) that finishes last merges that unit's partials itself.  pli_decode_splitkv
@@ -202,7 +203,8 @@ typedef struct pli_peer_scatter {
     int64_t slice_offset;
     /* pli_decode_fwd_gather only (may be NULL for the calls above): */
     uint32_t* peer_ready[PLI_MAX_PEERS];   /* rank r's array of n_peers zero-initialised "ready to receive" words */
-    uint32_t* cta_counter;                 /* LOCAL zero-initialised device word (CTAs of the running grid that finished) */
+    uint32_t* cta_counter;                 /* LOCAL zero-initialised device word; only read by builds that publish from the
+                                              decode grid's last CTA (-DPLI_PUBLISH_FROM_LAST_CTA=1), may be NULL otherwise */
 } pli_peer_scatter;
 int pli_decode_fwd_scatter(const void* q, const void* k_store, const void* v_store, const int32_t* block_table,
                            const int32_t* seq_lens, float* lse, int B, int Hq, int Hkv, int D, int max_seq_len,

@@ -285,6 +285,8 @@ struct DecodeTmaParams {
 //                               was never used (the caller's workspace needs NO initialisation): a compare-and-swap loop
 //                               that treats a word left by anything but this launch as zero.  37 CTAs contending on one
 //                               CAS cost ~25 us, which is why this is not the steady-state protocol.
+// (Never-used memory passes for a tagged word with probability 2^-40 per counter; a launch that died half-way leaves the
+// context unusable anyway.  Launches that share a workspace must be ordered, e.g. on one stream.)
 // Both atomics are acq_rel at device scope: they release this CTA's partials (ordered before them by the CTA barrier) and
 // acquire those of the splits that arrived earlier.
 constexpr unsigned long long kCtrTag = 0xA5C3D2E1F0ull << 24;       // upper 40 bits; arrivals in the lower 24
@@ -1129,6 +1131,8 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
     if (workspace == nullptr || workspace_bytes < pli_decode_workspace_bytes(B, Hq, D, num_splits))
         return set_error(PLI_ERR_INVALID, "workspace too small: need %zu bytes",
                          pli_decode_workspace_bytes(B, Hq, D, num_splits));
+    if (reinterpret_cast<uintptr_t>(workspace) & 15)      // the merge bulk-copies partials out of it; counters are 8-byte words
+        return set_error(PLI_ERR_INVALID, "workspace must be 16-byte aligned");
     float* o_part = static_cast<float*>(workspace);
     float* lse_part = o_part + (size_t)B * Hq * num_splits * D;
     const int G = Hq / Hkv;
@@ -1341,7 +1345,8 @@ extern "C" int pli_decode_fwd_gather(const void* q, const void* k_store, const v
     if (!ps || !o_strides || !q_strides || !kv_strides) return set_error(PLI_ERR_INVALID, "null argument");
     if (ps->n_peers < 1 || ps->n_peers > PLI_MAX_PEERS) return set_error(PLI_ERR_INVALID, "n_peers must be in [1, %d]", PLI_MAX_PEERS);
     if (ps->rank < 0 || ps->rank >= ps->n_peers) return set_error(PLI_ERR_INVALID, "rank outside [0, n_peers)");
-    if (!ps->epoch || !ps->cta_counter) return set_error(PLI_ERR_INVALID, "null epoch / cta_counter word");
+    if (!ps->epoch || (kPublishFromLastCta && !ps->cta_counter))
+        return set_error(PLI_ERR_INVALID, "null epoch / cta_counter word");
     if (ps->buffer_stride != 0)
         return set_error(PLI_ERR_INVALID, "the single-launch gather writes ONE buffer per rank: buffer_stride must be 0");
     if (!tma_path_ok(q, k_store, v_store, D, dtype, block_size, block_table != nullptr, q_strides, kv_strides, scale))
