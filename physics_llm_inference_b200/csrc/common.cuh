@@ -480,6 +480,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
     return r;
 }
+// distributed shared memory: a 32-bit load through a shared::cluster address (mapa_u32)
+__device__ __forceinline__ float ld_shared_cluster_f32(uint32_t cluster_addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }

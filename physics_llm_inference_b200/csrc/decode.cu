@@ -275,6 +275,8 @@ struct DecodeTmaParams {
     void* o_final;                  // with osb / osh; unused when peer.n > 0
     float* lse_final;               // or NULL
     PeerGather gather;
+    int cluster;                    // 2, 4, 8: the S = cluster splits of a unit form a thread-block cluster and are merged
+                                    // through distributed shared memory (no partials in global memory, no counters); else 1
     int peer_vec;                   // the peers' slices can be written with 16-byte stores (alignment checked on the host)
 };
 
@@ -434,6 +436,12 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
     constexpr int kTileBytes = kHalves * kSubTile;            // K (or V) bytes per stage
     constexpr int kNT = kD / 8;                               // PV n-tiles
     constexpr int kRowSlots = kRows16 ? 2 : 1;
+    // regions of the (then idle) K/V ring reused after the last stage: cross-warp merge area, bf16 staging of the peer
+    // stores, cluster exchange area -- all inside the ring for both head dims (D 64: 27.9 of 48 KiB)
+    constexpr int kMergeBytes = (128 + 64 * (kD + 8)) * 4;
+    constexpr int kStageOOffset = (kMergeBytes + 1023) & ~1023;
+    constexpr int kXchgOffset = kStageOOffset + 4096;
+    static_assert(kXchgOffset + 16 * kD * 4 + 64 <= 2 * kDecodeStages * kTileBytes, "epilogue regions must fit the K/V ring");
     using elem_t = typename std::conditional<kBf16, __nv_bfloat16, __half>::type;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -717,7 +725,9 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         // four elements per thread and pass, written as four independent chains (shared-memory reads, exp2, reciprocal,
         // store): one element at a time was ~600 dependent cycles per element and warp, 2400 of a short kernel's tail
         if (p.gather.n > 0 && p.o_direct != nullptr) mbar_wait(peer_ok, 0);      // the peers' buffers may be written
-        elem_t* stage_o = reinterpret_cast<elem_t*>(smem + 48 * 1024);           // [rows][kD], behind the merge area
+        elem_t* stage_o = reinterpret_cast<elem_t*>(smem + kStageOOffset);       // [rows][kD], behind the merge area
+        float* xo = reinterpret_cast<float*>(smem + kXchgOffset);                // cluster exchange: [16 rows][kD] + [16] LSEs
+        float* xl = xo + 16 * kD;
         constexpr int kIlp = 4;
         for (int base = tid; base < rows_here * kD; base += kIlp * kConsumerWarps * 32) {
             float o_val[kIlp], lse_val[kIlp];
@@ -759,6 +769,9 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                     // single split: this CTA owns the whole sequence, so the combine pass is skipped
                     reinterpret_cast<elem_t*>(p.o_direct)[b * p.osb + (h_base + row) * p.osh + d] = from_f32<elem_t>(o_val[u]);
                     if (d == 0 && p.lse_direct != nullptr) p.lse_direct[(int64_t)b * p.Hq + h_base + row] = lse_val[u];
+                } else if (p.cluster > 1) {
+                    xo[idx] = o_val[u];                          // read by the CTAs of this unit's cluster (below)
+                    if (d == 0) xl[row] = lse_val[u];
                 } else {
                     const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
                     p.o_part[prow * kD + d] = o_val[u];
@@ -831,6 +844,51 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 }
             }
         }
+    }
+    if (p.cluster > 1) {
+        // ---- the unit's S = cluster splits merge through distributed shared memory ----
+        // Every CTA has left its normalised partial (O, LSE) in its own shared memory (xo / xl).  After the cluster barrier
+        // (ALL threads of all CTAs take part, producers included) CTA r merges the r-th slice of the unit's rows_here x kD
+        // outputs, reading the S partial values of an element from the S CTAs; a second barrier keeps every CTA's shared
+        // memory alive until its neighbours have read it.  Against partials in global memory + arrival atomic + bulk copy
+        // this removes two L2 round trips and a device-scope release from the tail of the last CTA.
+        cluster_sync_all();
+        if (warp < kConsumerWarps) {
+            const int C = p.cluster, r = (int)cluster_ctarank();
+            const int total = rows_here * kD, per = (total + C - 1) / C;
+            const uint32_t xo_addr = smem_u32(smem + kXchgOffset), xl_addr = xo_addr + 16 * kD * 4;
+            if (p.gather.n > 0) mbar_wait(peer_ok, 0);
+            for (int e = r * per + (int)threadIdx.x; e < min(total, (r + 1) * per); e += kConsumerWarps * 32) {
+                const int row = e / kD, d = e - row * kD;
+                float lj[8], oj[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    lj[j] = j < C ? ld_shared_cluster_f32(mapa_u32(xl_addr + row * 4, j)) : -INFINITY;
+                    oj[j] = j < C ? ld_shared_cluster_f32(mapa_u32(xo_addr + e * 4, j)) : 0.f;
+                }
+                float M = lj[0];
+#pragma unroll
+                for (int j = 1; j < 8; ++j) M = fmaxf(M, lj[j]);
+                float den = 0.f, o = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float w = lj[j] == -INFINITY ? 0.f : __expf(lj[j] - M);
+                    den += w;
+                    o = fmaf(w, oj[j], o);
+                }
+                const elem_t val = from_f32<elem_t>(den > 0.f ? o / den : 0.f);
+                const int64_t off = b * p.osb + (h_base + row) * p.osh + d;
+                if (p.peer.n > 0) {
+                    const int64_t poff = p.peer.base() + off;
+                    for (int q = 0; q < p.peer.n; ++q) reinterpret_cast<elem_t*>(p.peer.o[q])[poff] = val;
+                } else {
+                    reinterpret_cast<elem_t*>(p.o_final)[off] = val;
+                }
+                if (d == 0 && p.lse_final != nullptr)
+                    p.lse_final[(int64_t)b * p.Hq + h_base + row] = den > 0.f ? M + logf(den) : -INFINITY;
+            }
+        }
+        cluster_sync_all();
     }
 }
 
@@ -1025,7 +1083,24 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
     if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, (int)smem));
     PLI_CUDA_CHECK(bind_status_symbol());
-    kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
+    if (p.cluster > 1) {
+        // the splits of a unit (consecutive blockIdx.x) are one thread-block cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kDecodeThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mk, mv, p));
+    } else {
+        kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
+    }
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();
     return PLI_OK;
@@ -1103,6 +1178,10 @@ static int check_decode_args(const void* q, const void* k, const void* v, const 
     return PLI_OK;
 }
 
+#ifndef PLI_CLUSTER_MERGE
+#define PLI_CLUSTER_MERGE 1
+#endif
+static constexpr bool kClusterMerge = PLI_CLUSTER_MERGE != 0;
 #ifndef PLI_PUBLISH_FROM_LAST_CTA
 #define PLI_PUBLISH_FROM_LAST_CTA 0
 #endif
@@ -1183,6 +1262,9 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
         }
         p.gather = PeerGather{};
         if ((direct || fused) && peer != nullptr && gather != nullptr) p.gather = *gather;
+        // 2, 4 or 8 splits: one thread-block cluster per unit, merged through distributed shared memory
+        p.cluster = (fused && kClusterMerge && (num_splits == 2 || num_splits == 4 || num_splits == 8)) ? num_splits : 1;
+        if (p.cluster > 1) p.counters = nullptr;
         if (wrote_direct) *wrote_direct = direct || fused;
         p.qsb = q_strides[0];
         p.qsh = q_strides[1];

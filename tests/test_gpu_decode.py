@@ -260,7 +260,7 @@ def test_mixed_prefill_decode_batch():
         at += n
 
 
-@pytest.mark.parametrize("splits", [None, 3])
+@pytest.mark.parametrize("splits", [None, 3, 4])
 def test_decode_peer_output_single_rank(splits):
     """The fused-gather entry with a world of one: same result as flash_decode, over several steps (buffers
     alternate by epoch), through both the direct-output kernel and the combine kernel."""
@@ -339,7 +339,9 @@ def test_decode_plan_matches_flash_decode_and_replays_in_a_graph():
 
 @pytest.mark.parametrize("B,G,D,L,splits", [(1, 4, 128, 32768, 37), (3, 8, 64, 5000, 64), (2, 16, 128, 2000, 5),
                                             (4, 32, 128, 777, 3),
-                                            (2, 16, 128, 4500, 64)])     # 16 rows x 64 splits x 512 B: merged in three groups
+                                            (2, 16, 128, 4500, 64),      # 16 rows x 64 splits x 512 B: merged in three groups
+                                            (2, 4, 128, 3000, 4), (2, 8, 64, 3000, 8), (1, 16, 128, 2000, 2),
+                                            (3, 32, 128, 1500, 8)])      # 2 / 4 / 8 splits: one cluster per unit (DSMEM merge)
 def test_fused_combine_matches_the_two_pass_path_on_a_dirty_workspace(B, G, D, L, splits):
     """Several splits per sequence: the split-KV kernel's last-arriving CTA of every unit merges the partials itself (no
     combine launch).  Its arrival counters live in the caller's workspace and need no initialisation: the same answer
