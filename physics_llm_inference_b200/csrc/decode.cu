@@ -275,8 +275,9 @@ struct DecodeTmaParams {
     void* o_final;                  // with osb / osh; unused when peer.n > 0
     float* lse_final;               // or NULL
     PeerGather gather;
-    int cluster;                    // 2, 4, 8: the S = cluster splits of a unit form a thread-block cluster and are merged
-                                    // through distributed shared memory (no partials in global memory, no counters); else 1
+    int cluster;                    // 2, 4, 8: `cluster` consecutive splits of a unit form a thread-block cluster and are
+                                    // merged through distributed shared memory; else 1
+    int parts;                      // partials per unit that go through global memory: S / cluster (1: none, no counters)
     int peer_vec;                   // the peers' slices can be written with 16-byte stores (alignment checked on the host)
 };
 
@@ -333,19 +334,19 @@ __device__ __forceinline__ void combine_fetch(const DecodeTmaParams& p, uint8_t*
     // the partials were written through the generic proxy (by other CTAs, acquired by this thread's arrival); the bulk
     // copy reads them, and overwrites shared memory this CTA has just read, through the async proxy
     fence_proxy_async_all();
-    const uint32_t total = (uint32_t)(nr * p.S * kD * 4);
+    const uint32_t total = (uint32_t)(nr * p.parts * kD * 4);
     mbar_arrive_expect_tx(bar, total);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.o_part + ((int64_t)b * p.Hq + h_base + r0) * p.S * kD);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.o_part + ((int64_t)b * p.Hq + h_base + r0) * p.parts * kD);
     for (uint32_t off = 0; off < total; off += 32768u) bulk_load(smem + off, src + off, min(32768u, total - off), bar);
 }
 __device__ __forceinline__ int combine_rows_per_group(const DecodeTmaParams& p, int kD, int ring_bytes, int rows_here) {
-    return max(1, min(rows_here, ring_bytes / (p.S * kD * 4)));
+    return max(1, min(rows_here, ring_bytes / (p.parts * kD * 4)));
 }
 
 template <int kD, typename elem_t>
 __device__ __forceinline__ void combine_unit(const DecodeTmaParams& p, uint8_t* smem, uint64_t* bar, int ring_bytes, int b,
                                              int h_base, int rows_here, int tid) {
-    const int S = p.S;
+    const int S = p.parts;
     constexpr int kVec = kD / 4;                                  // lanes per row: 32 (D 128) or 16 (D 64), 16 bytes each
     constexpr int kPerLane = 64 / kVec;                           // LSEs per lane (S <= 64)
     const int lane_in_row = tid % kVec;
@@ -520,6 +521,35 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
     // scheduled as soon as every CTA of this grid is running; it still waits for this grid's completion and memory
     // flush in its own griddepcontrol.wait, so only its launch latency is hidden.  No-op without a dependent.
     pdl_launch_dependents();
+
+    // ---- fused combine (consumer warps): this CTA's partial (or its cluster's) is in global memory; arrive on the unit's
+    // counter, and if this was the last of the unit's p.parts partials, merge them all into the final output ----
+    // (the partial stores of the 128 threads -- or, through the cluster barrier, of the whole cluster -- happen before
+    // thread 0's release; the merge reads the partial outputs through thread 0's bulk copy, issued behind its acquire and a
+    // proxy fence, and the partial LSEs with ld.global.cg, i.e. from L2, after the barrier that follows the acquire)
+    auto arrive_and_merge = [&]() {
+        const int tid = threadIdx.x;
+        int* is_last = reinterpret_cast<int*>(empty_bar + kDecodeStages);
+        named_bar_sync(1, kConsumerWarps * 32);
+        unsigned long long* ctr = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);
+        bool tagged = false;
+        if (tid == 0) {
+            const bool last = unit_arrive(ctr, p.launch_id, tagged) == (uint32_t)p.parts - 1u;
+            *is_last = last;
+            // (every consumer thread is past its last read of the merge area: the barrier above) the first group of the
+            // unit's partials is requested before the other threads even learn that this CTA merges
+            if (last)
+                combine_fetch<kD>(p, smem, merge_bar, b, h_base, 0,
+                                  min(rows_here, combine_rows_per_group(p, kD, 2 * kDecodeStages * kTileBytes, rows_here)));
+        }
+        named_bar_sync(1, kConsumerWarps * 32);
+        if (*is_last) {
+            if (p.gather.n > 0) mbar_wait(peer_ok, 0);
+            combine_unit<kD, elem_t>(p, smem, merge_bar, 2 * kDecodeStages * kTileBytes, b, h_base, rows_here, tid);
+            if (tid == 0) unit_reset(ctr, p.launch_id, tagged);
+            if (threadIdx.x == 0) PLI_DECODE_TRACE(5);       // combined output written
+        }
+    };
 
     if (warp >= kConsumerWarps) {
         // ===================== producer warps: TMA page loads (warp 4: K tiles, warp 5: V tiles) =====================
@@ -773,7 +803,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                     xo[idx] = o_val[u];                          // read by the CTAs of this unit's cluster (below)
                     if (d == 0) xl[row] = lse_val[u];
                 } else {
-                    const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.S + s;
+                    const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.parts + s;
                     p.o_part[prow * kD + d] = o_val[u];
                     if (d == 0) p.lse_part[prow] = lse_val[u];
                 }
@@ -792,32 +822,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             }
         }
         if (threadIdx.x == 0) PLI_DECODE_TRACE(4);               // output / partial written
-        if (p.counters != nullptr) {
-            // ---- fused combine: the last split of this unit to arrive merges all of them ----
-            // (the partial stores of all 128 threads happen before thread 0's release through the CTA barrier; the merge
-            // reads the partial outputs through thread 0's bulk copy, issued behind its acquire and a proxy fence, and
-            // the partial LSEs with ld.global.cg, i.e. from L2, after the barrier that follows the acquire)
-            int* is_last = reinterpret_cast<int*>(empty_bar + kDecodeStages);
-            named_bar_sync(1, kConsumerWarps * 32);
-            unsigned long long* ctr = p.counters + 2 * ((int64_t)b * gridDim.y + blockIdx.y);
-            bool tagged = false;
-            if (tid == 0) {
-                const bool last = unit_arrive(ctr, p.launch_id, tagged) == (uint32_t)p.S - 1u;
-                *is_last = last;
-                // (every consumer thread is past its last read of the merge area: the barrier above) the first group of the
-                // unit's partials is requested before the other threads even learn that this CTA merges
-                if (last)
-                    combine_fetch<kD>(p, smem, merge_bar, b, h_base, 0,
-                                      min(rows_here, combine_rows_per_group(p, kD, 2 * kDecodeStages * kTileBytes, rows_here)));
-            }
-            named_bar_sync(1, kConsumerWarps * 32);
-            if (*is_last) {
-                if (p.gather.n > 0) mbar_wait(peer_ok, 0);
-                combine_unit<kD, elem_t>(p, smem, merge_bar, 2 * kDecodeStages * kTileBytes, b, h_base, rows_here, tid);
-                if (tid == 0) unit_reset(ctr, p.launch_id, tagged);
-                if (threadIdx.x == 0) PLI_DECODE_TRACE(5);       // combined output written
-            }
-        }
+        if (p.parts > 1 && p.cluster == 1) arrive_and_merge();
         if (p.gather.n > 0 && p.gather.cta_counter != nullptr) {
             // ---- (option, off: see pli_decode_fwd_gather) the last CTA of the grid to get here publishes this rank's
             // slice and waits for the peers' ----
@@ -857,7 +862,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             const int C = p.cluster, r = (int)cluster_ctarank();
             const int total = rows_here * kD, per = (total + C - 1) / C;
             const uint32_t xo_addr = smem_u32(smem + kXchgOffset), xl_addr = xo_addr + 16 * kD * 4;
-            if (p.gather.n > 0) mbar_wait(peer_ok, 0);
+            if (p.gather.n > 0 && p.parts == 1) mbar_wait(peer_ok, 0);
             for (int e = r * per + (int)threadIdx.x; e < min(total, (r + 1) * per); e += kConsumerWarps * 32) {
                 const int row = e / kD, d = e - row * kD;
                 float lj[8], oj[8];
@@ -876,7 +881,16 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                     den += w;
                     o = fmaf(w, oj[j], o);
                 }
-                const elem_t val = from_f32<elem_t>(den > 0.f ? o / den : 0.f);
+                const float on = den > 0.f ? o / den : 0.f;
+                const float ln = den > 0.f ? M + logf(den) : -INFINITY;
+                if (p.parts > 1) {
+                    // several clusters per unit: this cluster's merged partial goes through the workspace
+                    const int64_t prow = ((int64_t)b * p.Hq + h_base + row) * p.parts + blockIdx.x / C;
+                    p.o_part[prow * kD + d] = on;
+                    if (d == 0) p.lse_part[prow] = ln;
+                    continue;
+                }
+                const elem_t val = from_f32<elem_t>(on);
                 const int64_t off = b * p.osb + (h_base + row) * p.osh + d;
                 if (p.peer.n > 0) {
                     const int64_t poff = p.peer.base() + off;
@@ -884,11 +898,12 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
                 } else {
                     reinterpret_cast<elem_t*>(p.o_final)[off] = val;
                 }
-                if (d == 0 && p.lse_final != nullptr)
-                    p.lse_final[(int64_t)b * p.Hq + h_base + row] = den > 0.f ? M + logf(den) : -INFINITY;
+                if (d == 0 && p.lse_final != nullptr) p.lse_final[(int64_t)b * p.Hq + h_base + row] = ln;
             }
         }
+        // (also: the slices of a cluster partial written by the other CTAs happen before rank 0's arrival below)
         cluster_sync_all();
+        if (p.parts > 1 && warp < kConsumerWarps && cluster_ctarank() == 0) arrive_and_merge();
     }
 }
 
@@ -1075,7 +1090,7 @@ int make_kv_map(CUtensorMap* map, const void* base, int dtype, int D, int Hkv, b
 }
 
 template <int kD, bool kBf16, bool kRows16>
-int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaParams& p, dim3 grid, cudaStream_t stream) {
+int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, DecodeTmaParams p, dim3 grid, cudaStream_t stream) {
     auto kern = decode_tma_kernel<kD, kBf16, kRows16>;
     constexpr int kTileBytes = (kD / 64) * kStageTokens * 128;
     const size_t merge_bytes = (size_t)(128 + 64 * (kD + 8)) * sizeof(float);
@@ -1083,6 +1098,34 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, const DecodeTmaPa
     if (smem < merge_bytes + 1024) smem = merge_bytes + 1024;
     PLI_CUDA_CHECK(ensure_dynamic_smem(kern, (int)smem));
     PLI_CUDA_CHECK(bind_status_symbol());
+    if (p.cluster > 1) {
+        // A grid that fits the GPU in one wave as independent CTAs may not fit as clusters (the CTAs of a cluster need free
+        // slots inside one GPC): 288 CTAs in clusters of four ran as two waves, 40.9 us instead of 28.6.  Ask the runtime
+        // how many clusters can be resident and merge through the workspace instead when the grid would not fit.
+        static int max_active[9] = {0};                     // per cluster size, this kernel instance (benign race: same value)
+        if (max_active[p.cluster] == 0) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3((unsigned)p.cluster, 1, 1);
+            q.blockDim = dim3(kDecodeThreads);
+            q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = (unsigned)p.cluster;
+            qa[0].val.clusterDim.y = 1;
+            qa[0].val.clusterDim.z = 1;
+            q.attrs = qa;
+            q.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = -1; }
+            max_active[p.cluster] = n;
+        }
+        const long long ctas = (long long)grid.x * grid.y * grid.z;
+        const int sms = sm_count() > 0 ? sm_count() : 148;
+        if (max_active[p.cluster] < 0 || (ctas <= 2LL * sms && ctas / p.cluster > max_active[p.cluster])) {
+            p.cluster = 1;
+            p.parts = p.S;
+        }
+    }
     if (p.cluster > 1) {
         // the splits of a unit (consecutive blockIdx.x) are one thread-block cluster
         cudaLaunchConfig_t cfg = {};
@@ -1145,6 +1188,9 @@ extern "C" int pli_decode_num_splits(int B, int Hkv, int max_seq_len) {
     int s = by_fill < by_len ? by_fill : by_len;
     if (s < 1) s = 1;
     if (s > 64) s = 64;
+    // more than eight splits: a multiple of eight, so that eight at a time merge inside a thread-block cluster (through
+    // distributed shared memory) and only s / 8 partials per unit go through the workspace
+    if (s > 8) s &= ~7;
     return s;
 }
 
@@ -1263,8 +1309,9 @@ static int splitkv_impl(const void* q, const void* k_store, const void* v_store,
         p.gather = PeerGather{};
         if ((direct || fused) && peer != nullptr && gather != nullptr) p.gather = *gather;
         // 2, 4 or 8 splits: one thread-block cluster per unit, merged through distributed shared memory
-        p.cluster = (fused && kClusterMerge && (num_splits == 2 || num_splits == 4 || num_splits == 8)) ? num_splits : 1;
-        if (p.cluster > 1) p.counters = nullptr;
+        p.cluster = 1;
+        if (fused && kClusterMerge) p.cluster = num_splits % 8 == 0 ? 8 : num_splits % 4 == 0 ? 4 : num_splits % 2 == 0 ? 2 : 1;
+        p.parts = fused ? num_splits / p.cluster : num_splits;
         if (wrote_direct) *wrote_direct = direct || fused;
         p.qsb = q_strides[0];
         p.qsh = q_strides[1];

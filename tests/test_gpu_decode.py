@@ -341,7 +341,9 @@ def test_decode_plan_matches_flash_decode_and_replays_in_a_graph():
                                             (4, 32, 128, 777, 3),
                                             (2, 16, 128, 4500, 64),      # 16 rows x 64 splits x 512 B: merged in three groups
                                             (2, 4, 128, 3000, 4), (2, 8, 64, 3000, 8), (1, 16, 128, 2000, 2),
-                                            (3, 32, 128, 1500, 8)])      # 2 / 4 / 8 splits: one cluster per unit (DSMEM merge)
+                                            (3, 32, 128, 1500, 8),       # 2 / 4 / 8 splits: one cluster per unit (DSMEM merge)
+                                            (1, 4, 128, 32768, 32), (2, 8, 64, 6000, 24), (2, 16, 128, 3000, 12),
+                                            (3, 4, 128, 2500, 6), (1, 4, 128, 9000, 40)])   # clusters, then partials of clusters
 def test_fused_combine_matches_the_two_pass_path_on_a_dirty_workspace(B, G, D, L, splits):
     """Several splits per sequence: the split-KV kernel's last-arriving CTA of every unit merges the partials itself (no
     combine launch).  Its arrival counters live in the caller's workspace and need no initialisation: the same answer
