@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
             }
         }
         if (threadIdx.x == 0) PLI_DECODE_TRACE(4);               // output / partial written
-        if (p.parts > 1 && p.cluster == 1) arrive_and_merge();
+        if (p.counters != nullptr && p.parts > 1 && p.cluster == 1) arrive_and_merge();   // (NULL: partials only)
         if (p.gather.n > 0 && p.gather.cta_counter != nullptr) {
             // ---- (option, off: see pli_decode_fwd_gather) the last CTA of the grid to get here publishes this rank's
             // slice and waits for the peers' ----
@@ -903,7 +903,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
         }
         // (also: the slices of a cluster partial written by the other CTAs happen before rank 0's arrival below)
         cluster_sync_all();
-        if (p.parts > 1 && warp < kConsumerWarps && cluster_ctarank() == 0) arrive_and_merge();
+        if (p.counters != nullptr && p.parts > 1 && warp < kConsumerWarps && cluster_ctarank() == 0) arrive_and_merge();
     }
 }
 
