@@ -122,6 +122,14 @@ __global__ void __launch_bounds__(128) decode_simt_kernel(
 // ------------------------------------------------------------------------------------------------
 // TMA + mma.sync split-KV kernel
 // ------------------------------------------------------------------------------------------------
+// Option (off): launch the split-KV kernel programmatically behind its predecessor on the stream (launch_tma_t; its first
+// statement is griddepcontrol.wait, so only launch latency is hidden).  Eager steps gain ~2 us (C5 share 25.5 -> 23.6 us,
+// batch 8 x 8k 46.5 -> 44.3), graph replays nothing, and the clustered many-split case loses 6 us (one 32k sequence: 27.6
+// -> 33.5 us graph, 29.8 -> 37.0 eager): the early-resident dependent grid gets in the way of the running grid's clusters.
+#ifndef PLI_DECODE_PDL
+#define PLI_DECODE_PDL 0
+#endif
+constexpr bool kDecodePdl = PLI_DECODE_PDL != 0;
 constexpr int kStageTokens = 64;   // tokens per pipeline stage (16 per consumer warp)
 constexpr int kDecodeStages = 3;   // smem ring depth (3 x 32 KB at D=128 -> 2 CTAs per SM)
 constexpr int kConsumerWarps = 4;
@@ -459,6 +467,7 @@ __global__ void __launch_bounds__(kDecodeThreads) decode_tma_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int s = blockIdx.x, b = blockIdx.z;
     const int hk = blockIdx.y % p.Hkv, hchunk = blockIdx.y / p.Hkv;   // hchunk: 16-row groups when G > 16
+    pdl_wait();                                                       // (see launch_tma_t) no-op for a plain launch
     if (threadIdx.x == 0) PLI_DECODE_TRACE(0);                        // CTA start
     // The parameter block spans several 64-byte lines of the constant bank; one lane per warp touches a line each, so
     // that first-use misses later in the kernel (~600 cycles each) are all in flight together here.
@@ -1126,23 +1135,33 @@ int launch_tma_t(const CUtensorMap& mk, const CUtensorMap& mv, DecodeTmaParams p
             p.parts = p.S;
         }
     }
-    if (p.cluster > 1) {
-        // the splits of a unit (consecutive blockIdx.x) are one thread-block cluster
+    {
+        // Launched programmatically behind whatever precedes it on the stream: the kernel's first statement is
+        // griddepcontrol.wait, so every dependency is kept and only the launch latency is hidden (the grid is resident
+        // and waiting when its predecessor ends).  With 2 / 4 / 8 splits per unit the splits of a unit (consecutive
+        // blockIdx.x) are one thread-block cluster.
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = grid;
         cfg.blockDim = dim3(kDecodeThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)p.cluster;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
+        cudaLaunchAttribute attr[2];
+        int na = 0;
+        if (kDecodePdl) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+        }
+        if (p.cluster > 1) {
+            attr[na].id = cudaLaunchAttributeClusterDimension;
+            attr[na].val.clusterDim.x = (unsigned)p.cluster;
+            attr[na].val.clusterDim.y = 1;
+            attr[na].val.clusterDim.z = 1;
+            ++na;
+        }
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = na;
         PLI_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, mk, mv, p));
-    } else {
-        kern<<<grid, kDecodeThreads, smem, stream>>>(mk, mv, p);
     }
     PLI_CUDA_CHECK(cudaGetLastError());
     count_launch();
