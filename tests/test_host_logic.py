@@ -43,6 +43,14 @@ def test_workspace_and_split_helpers_need_no_gpu():
     assert lib.pli_decode_workspace_bytes(64, 32, 128, 4) == 64 * 32 * 4 * 129 * 4 + 64 * 32 * 16
     assert lib.pli_decode_workspace_bytes(1, 1, 64, 1) == 264 + 16
     assert lib.pli_decode_workspace_bytes(0, 32, 128, 4) == 0
+    # split counts (148 SMs assumed without a device): one wave of CTAs, >= 256 tokens per split, counts above eight are
+    # multiples of eight (eight splits at a time merge inside a thread-block cluster)
+    assert lib.pli_decode_num_splits(256, 1, 1024) == 1
+    assert lib.pli_decode_num_splits(64, 8, 4096) == 1
+    assert lib.pli_decode_num_splits(8, 8, 8192) == 4
+    assert lib.pli_decode_num_splits(4, 8, 16384) == 8
+    assert lib.pli_decode_num_splits(1, 8, 32768) == 32
+    assert lib.pli_decode_num_splits(1, 8, 700) == 3
 
 
 def test_config_defaults_match_reference(golden_dir):
