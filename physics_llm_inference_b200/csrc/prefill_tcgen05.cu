@@ -73,6 +73,9 @@ static_assert(kSpecCols == 0 || kSpecCols == 8 || kSpecCols == 16 || kSpecCols =
 // (profiles/r02_ab_warp_epilogue.log).  The in-kernel timeline shows why: the 2200-2900 cycles between "epilogue start" and
 // "epilogue done" of a tile are mostly the wait for the item's last PV to complete, not the conversion and the stores.
 // Default: the round-1 epilogue (a 64-column half of the tile at a time through one 16 KiB buffer).
+#ifndef PLI_KV_SUSPEND_NS
+#define PLI_KV_SUSPEND_NS 1000         // suspend-time hint of the TMA producers' wait for a free K/V ring slot
+#endif
 #ifndef PLI_LD64
 #define PLI_LD64 0                     // the softmax warps read a half-step's 64 scores with one tcgen05.ld.x64 instead of two x32
 #endif
@@ -1101,7 +1104,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         return;
                     }
                     const uint32_t slot = kv_cnt % kRing;
-                    mbar_wait_relaxed(&kv_empty[slot], ((kv_cnt / kRing) & 1) ^ 1);
+                    mbar_wait_relaxed<PLI_KV_SUSPEND_NS>(&kv_empty[slot], ((kv_cnt / kRing) & 1) ^ 1);
                     if constexpr (kPairMma) {
                         // this CTA's half of the B operand, reported to the leader's barrier (lane 0 only runs this):
                         // K: keys [64 h + 32 rank, +32) of both half-steps h (map_k carries 32-row boxes);

@@ -15,6 +15,21 @@ q = torch.randn(B, Hq, N, D, device="cuda").bfloat16()
 k = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
 v = torch.randn(B, Hkv, N, D, device="cuda").bfloat16()
 lib = _lib.load()
+PAGED = os.environ.get("PLI_TRACE_PAGED") == "1"          # C2 read in place from 16-token pages (the kPaged instance)
+if PAGED:
+    bs_ = 16
+    P_ = B * N // bs_
+    kp_ = torch.randn(P_, 1, bs_, Hkv, D, device="cuda").bfloat16()
+    vp_ = torch.randn(P_, 1, bs_, Hkv, D, device="cuda").bfloat16()
+    table_ = torch.randperm(P_).to(torch.int32).view(B, N // bs_).cuda()
+    lens_ = torch.full((B,), N, dtype=torch.int32, device="cuda")
+
+    class _Paged:
+        @staticmethod
+        def flash_attention_forward(q_, k_, v_, causal=True):
+            return _real.flash_attention_paged(q_, kp_, vp_, table_, lens_, max_seq_len=N)
+    _real = pli
+    pli = _Paged
 for _ in range(2):
     pli.flash_attention_forward(q, k, v, causal=True)
 cap = 20000
