@@ -260,7 +260,7 @@ def test_mixed_prefill_decode_batch():
         at += n
 
 
-@pytest.mark.parametrize("splits", [None, 3, 4])
+@pytest.mark.parametrize("splits", [None, 3, 4, 16])
 def test_decode_peer_output_single_rank(splits):
     """The fused-gather entry with a world of one: same result as flash_decode, over several steps (buffers
     alternate by epoch), through both the direct-output kernel and the combine kernel."""
