@@ -131,7 +131,13 @@ __global__ void __launch_bounds__(128) decode_simt_kernel(
 #endif
 constexpr bool kDecodePdl = PLI_DECODE_PDL != 0;
 constexpr int kStageTokens = 64;   // tokens per pipeline stage (16 per consumer warp)
-constexpr int kDecodeStages = 3;   // smem ring depth (3 x 32 KB at D=128 -> 2 CTAs per SM)
+#ifndef PLI_DECODE_STAGES
+#define PLI_DECODE_STAGES 3
+#endif
+// smem ring depth: 3 x 32 KB at D = 128 -> 2 CTAs per SM.  (6 stages and ONE CTA per SM -- the same bytes in flight, half
+// the partials -- measured 15-25 % slower everywhere: C5 share at 8k context 5757 against 6687 GB/s, one 32k sequence 31.3
+// against 27.6 us; four consumer warps and one producer pair per SM do not keep up.)
+constexpr int kDecodeStages = PLI_DECODE_STAGES;
 constexpr int kConsumerWarps = 4;
 constexpr int kProducerWarps = 2;  // warp 4 loads the K tiles, warp 5 the V tiles: issuing a TMA from lanes with different
                                    // operands costs ~70 cycles each (an elect / R2UR loop), 16 of them per 16-token-page stage
@@ -1200,7 +1206,7 @@ extern "C" int pli_decode_num_splits(int B, int Hkv, int max_seq_len) {
     // least 256 tokens per split.
     const int64_t units = (int64_t)B * Hkv;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    const int64_t target = (int64_t)sms * 2;
+    const int64_t target = (int64_t)sms * (PLI_DECODE_STAGES > 3 ? 1 : 2);
     // floor: 256 units on 296 CTA slots stay unsplit (measured B256/Hkv1/L1k: 1 split 34.5 us, 2 splits 41.9 us)
     int by_fill = (int)(target / units);
     int by_len = (max_seq_len + 255) / 256;
