@@ -1,17 +1,21 @@
-// decode.cu — split-KV decode attention over the ch02 contiguous cache / ch07 paged pools,
-// the log-sum-exp combine pass, the KV append (write path) and the page-gather parity aid.
+// decode.cu — split-KV decode attention over the ch02 contiguous cache / ch07 paged pools, the merge of the splits,
+// the KV append (write path), the page-gather parity aid and the NVLink gather of the output.
 //
 // Maths: ch02/cached_generation.py:72-94 for seq_len == 1 (no mask, :85) with the GQA map of
 // :77-78.  Addressing: ch07/paged_memory.py:38-48 pool layout, token t -> page table[t / bs],
 // slot t % bs (ceil-div rule, :54,:84-86).  HBM-bound: each K/V byte is read exactly once and all
 // q heads of a KV group are served from that one read.
 //
-// Two split-KV kernels write (normalised O, natural-log LSE) partials to the workspace:
-//   decode_tma_kernel   bf16/f16, head_dim 64/128, page size 2^k in [8,256] (or contiguous):
-//                       a producer warp streams 64-token K/V stages into a 128B-swizzled smem ring
-//                       with TMA (one box per page, page ids from the block table), four consumer
-//                       warps run QK^T and PV on mma.sync m16n8k16 via ldmatrix, fp32 softmax state.
-//   decode_simt_kernel  everything else (f32 storage, odd head_dim / page size): CUDA cores.
+//   decode_tma_kernel   bf16/f16, head_dim 64/128, page size 2^k in [8,256] (or contiguous): two producer warps stream
+//                       64-token K / V stages into a 128B-swizzled smem ring with TMA (one box per page, page ids from the
+//                       block table), four consumer warps run QK^T and PV on mma.sync m16n8k16 via ldmatrix, fp32 softmax
+//                       state.  ONE launch per decode call: a single split writes the output; 2 / 4 / 8 splits of a unit
+//                       form a thread-block cluster and merge through distributed shared memory; more splits leave
+//                       partials (of clusters of eight) in the workspace and the CTA that arrives last on the unit's
+//                       counter merges them.  With a peer table the final stores go to every rank's copy
+//                       of the output over NVLink (pli_decode_fwd_gather).
+//   decode_simt_kernel  everything else (f32 storage, odd head_dim / page size): CUDA cores, partials only.
+//   decode_combine_kernel  the two-launch form's merge of the partials (pli_decode_splitkv + pli_decode_combine; SIMT path).
 #include <atomic>
 #include <cstdlib>
 #include <type_traits>
