@@ -321,6 +321,18 @@ __device__ __forceinline__ void tma_load_4d_pair_hint(void* smem_dst, const CUte
         "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_pair_hint(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                      int c0, int c1, int c2, int c3, int c4, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;\n" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy)
+        : "memory");
+}
+// 16 bytes of zeros into the shared memory of another CTA of the cluster (shared::cluster address from mapa_u32)
+__device__ __forceinline__ void st_shared_cluster_zero16(uint32_t cluster_addr) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(cluster_addr), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_multicast_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
                                                            int c1, int c2, int c3, uint16_t cta_mask, uint64_t policy) {
     asm volatile(

@@ -73,6 +73,11 @@ static_assert(kSpecCols == 0 || kSpecCols == 8 || kSpecCols == 16 || kSpecCols =
 // (profiles/r02_ab_warp_epilogue.log).  The in-kernel timeline shows why: the 2200-2900 cycles between "epilogue start" and
 // "epilogue done" of a tile are mostly the wait for the item's last PV to complete, not the conversion and the stores.
 // Default: the round-1 epilogue (a 64-column half of the tile at a time through one 16 KiB buffer).
+// CTA-pair MMAs for the paged instance of the kernel (K/V halves assembled from page boxes, reported to the leader's barrier).
+#ifndef PLI_PAGED_PAIR_MMA
+#define PLI_PAGED_PAIR_MMA 1
+#endif
+constexpr bool kPagedPairMma = PLI_PAGED_PAIR_MMA != 0;
 #ifndef PLI_KV_SUSPEND_NS
 #define PLI_KV_SUSPEND_NS 1000         // suspend-time hint of the TMA producers' wait for a free K/V ring slot
 #endif
@@ -167,6 +172,7 @@ struct PrefillParams {
     const int32_t* table;
     const int32_t* seq_lens;
     int table_stride, page_size, page_shift, layer, box_rows;       // page_size and box_rows are powers of two
+    int box_rows_v;                   // pair MMAs over paged K/V: rows of a V box (box_rows: of a K box, <= 32)
     // ragged query lengths (paged kernels only): q / o are packed (total_q, Hq, D), rows [cu_q[b], cu_q[b+1]) belong
     // to sequence b; Nq is then the host's upper bound of the per-sequence lengths (it sizes the schedule)
     const int32_t* cu_q;
@@ -336,7 +342,7 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     constexpr int kStages = L::kKVStages;
     constexpr int kTileBytes = L::kTileBytes;
     constexpr int kHalves = kD / 64;
-    static_assert(!kPairMma || (kCluster == 2 && !kPaged && kD == 128), "pair MMAs: cluster of 2, contiguous K/V, D = 128");
+    static_assert(!kPairMma || (kCluster == 2 && kD == 128), "pair MMAs: cluster of 2, D = 128");
     constexpr int kRing = kPairMma ? 2 * kStages : kStages;              // K/V ring entries ...
     constexpr int kEntryBytes = kPairMma ? kTileBytes / 2 : kTileBytes;  // ... of this size (same total)
     constexpr int kMmaM = kPairMma ? 2 * kBM : kBM;
@@ -1005,6 +1011,23 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                         // memory before the first PV that reads the tile.  Both MMA warps do it (same zeros), each
                         // before its own MMAs.  K needs nothing: scores of those keys are replaced by select.
                         const int r0 = max(it.nk - (s >> 1) * kBN, 0);
+                        if constexpr (kPairMma) {
+                            // pair MMAs: this (leader) CTA and its peer each hold [128 keys][64 head_dim columns] of the tile;
+                            // the leader's MMA warp cleans both halves, the peer's through distributed shared memory
+                            if (h == 0 && r0 < kBN) {
+                                uint8_t* vt = sKV + slot_of(2 * (s >> 1) + 1) * kEntryBytes;
+                                const uint32_t vt_peer = mapa_u32(smem_u32(vt), 1);
+                                const int rows = kBN - r0;
+                                for (int idx = lane; idx < rows * 8; idx += 32) {
+                                    const int off = (r0 + (idx >> 3)) * 128 + (idx & 7) * 16;
+                                    *reinterpret_cast<uint4*>(vt + off) = make_uint4(0u, 0u, 0u, 0u);
+                                    st_shared_cluster_zero16(vt_peer + off);
+                                }
+                                asm volatile("fence.acq_rel.cluster;\n" ::: "memory");    // the peer's zeros are performed ...
+                                fence_proxy_async_all();                                   // ... before the MMAs read them
+                                __syncwarp();
+                            }
+                        } else
                         if (h == 0 && r0 < kBN) {
                             uint8_t* vt = sKV + slot_of(2 * (s >> 1) + 1) * kTileBytes;
                             const int rows = kBN - r0;
@@ -1091,8 +1114,14 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 // looked up once per tile j (K and V share it).  Boxes past the sequence end re-read the last valid
                 // page (the byte count per tile stays fixed; those keys are masked).
                 const int rows_cta = kBN / kCluster;
-                const int n_boxes = kPaged ? rows_cta / p.box_rows : 0;
-                const int row0 = rank * rows_cta + lane * p.box_rows;
+                // (pair MMAs: warp 14's lanes own the K boxes of this CTA's 32 keys of each half-step, warp 15's lanes the V
+                // boxes of all 128 keys -- this CTA's 64 head_dim columns of them)
+                const int n_boxes = !kPaged ? 0 : !kPairMma ? rows_cta / p.box_rows : do_k ? 64 / p.box_rows : kBN / p.box_rows_v;
+                int row0 = rank * rows_cta + lane * p.box_rows;
+                if constexpr (kPaged && kPairMma) {
+                    const int per_hh = 32 / p.box_rows;            // K boxes per half-step in this CTA
+                    row0 = do_k ? (lane / per_hh) * kHN + rank * 32 + (lane % per_hh) * p.box_rows : lane * p.box_rows_v;
+                }
                 auto page_of = [&](int j) -> int {
                     if (!kPaged || lane >= n_boxes) return 0;
                     const int key = max(min(j * kBN + row0, it.nk - 1), 0);
@@ -1105,7 +1134,32 @@ prefill_tcgen05_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                     }
                     const uint32_t slot = kv_cnt % kRing;
                     mbar_wait_relaxed<PLI_KV_SUSPEND_NS>(&kv_empty[slot], ((kv_cnt / kRing) & 1) ^ 1);
-                    if constexpr (kPairMma) {
+                    if constexpr (kPairMma && kPaged) {
+                        // pair MMAs over paged K/V: the same halves of the B operand as below, assembled from page boxes by
+                        // the lanes of this warp and reported to the leader's barrier
+                        if (rank == 0 && lane == 0) mbar_arrive_expect_tx(&kv_full[slot], 2 * kEntryBytes);
+                        __syncwarp();
+                        if (lane < n_boxes) {
+                            const uint32_t bar = kv_full_leader + slot * 8;
+                            const int brows = map == &map_k ? p.box_rows : p.box_rows_v;
+                            const int in_page = max(min(j * kBN + row0, it.nk - 1), 0) & (p.page_size - 1);
+                            const int slot0 = in_page & ~(brows - 1);                  // box-aligned slot inside the page
+                            uint8_t* dst = sKV + slot * kEntryBytes;
+                            if (map == &map_k) {
+                                const int per_hh = 32 / p.box_rows;
+                                const int hh = lane / per_hh, bi = lane % per_hh;
+#pragma unroll
+                                for (int hf = 0; hf < kHalves; ++hf)
+                                    tma_load_5d_pair_hint(dst + hf * (kSubTileBytes / 2) + (hh * 32 + bi * p.box_rows) * 128, map, bar,
+                                                          hf * 64, it.hk, slot0, p.layer, page, kHintKV);
+                            } else {
+                                tma_load_5d_pair_hint(dst + lane * p.box_rows_v * 128, map, bar, rank * 64, it.hk, slot0, p.layer, page,
+                                                      kHintKV);
+                            }
+                        }
+                        ++kv_cnt;
+                        return;
+                    } else if constexpr (kPairMma) {
                         // this CTA's half of the B operand, reported to the leader's barrier (lane 0 only runs this):
                         // K: keys [64 h + 32 rank, +32) of both half-steps h (map_k carries 32-row boxes);
                         // V: head_dim columns [64 rank, +64) of all 128 keys (map_v carries 128-row boxes)
@@ -2003,7 +2057,7 @@ void fill_schedule(PrefillParams& p, int B, int Hq, int Hkv, int Nq) {
 #endif
     p.table = nullptr;
     p.seq_lens = nullptr;
-    p.table_stride = p.page_size = p.page_shift = p.layer = p.box_rows = 0;
+    p.table_stride = p.page_size = p.page_shift = p.layer = p.box_rows = p.box_rows_v = 0;
     p.cu_q = nullptr;
     p.o_base = nullptr;
     p.o_st_tok = p.o_st_head = p.o_st_batch = 0;
@@ -2021,14 +2075,17 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
                                  int layer, int64_t num_pages, const int64_t* qs, const int64_t* kvs, const int64_t* os,
                                  float scale, int dtype, cudaStream_t stream) {
     const bool pairs = (Hq / Hkv) % 4 == 0 && cluster_mode_enabled();
-    const int rows_cta = pairs ? kHN : kBN;
+    // CTA-pair MMAs as in the contiguous kernel (D = 128): K boxes of at most 32 keys, V boxes of up to 128
+    const bool pair_mma = pairs && D == 128 && kPagedPairMma;
+    const int rows_cta = pair_mma ? 32 : pairs ? kHN : kBN;
     const int box_rows = block_size < rows_cta ? block_size : rows_cta;
+    const int box_rows_v = pair_mma ? (block_size < kBN ? block_size : kBN) : box_rows;
     CUtensorMap mq, mk, mv, mo;
     int rc;
     const bool packed = cu_seqlens_q != nullptr;
     if ((rc = make_map_4d(&mq, q, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, qs))) return rc;
     if ((rc = make_pool_map(&mk, k_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
-    if ((rc = make_pool_map(&mv, v_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows))) return rc;
+    if ((rc = make_pool_map(&mv, v_pool, dtype, D, Hkv, block_size, layer + 1, num_pages, kvs, box_rows_v))) return rc;
     if ((rc = make_map_4d(&mo, o, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, os))) return rc;
     PeerMaps pm = no_peers();
     if ((rc = make_map_4d(&pm.o32, o, dtype, D, packed ? (int)total_q : Nq, Hq, packed ? 1 : B, os, 32, 32))) return rc;
@@ -2052,6 +2109,7 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
     p.page_shift = block_size == 16 ? 4 : block_size == 32 ? 5 : block_size == 64 ? 6 : 7;
     p.layer = layer;
     p.box_rows = box_rows;
+    p.box_rows_v = box_rows_v;
     p.o_base = static_cast<uint8_t*>(o);
     p.o_st_batch = packed ? 0 : os[0];
     p.o_st_head = os[1];
@@ -2065,6 +2123,10 @@ int launch_prefill_tcgen05_paged(const void* q, const void* k_pool, const void* 
 #define PLI_GO(DD, BF)                                                                                  \
     return pairs ? launch_t<DD, BF, 2, true>(mq, mk, mv, mo, p, stream, pm) : launch_t<DD, BF, 1, true>(mq, mk, mv, mo, p, stream, pm)
     if (D == 128) {
+        if (pair_mma) {
+            if (bf16) return launch_t<128, true, 2, true, true>(mq, mk, mv, mo, p, stream, pm);
+            return launch_t<128, false, 2, true, true>(mq, mk, mv, mo, p, stream, pm);
+        }
         if (bf16) PLI_GO(128, true);
         PLI_GO(128, false);
     }
