@@ -368,7 +368,6 @@ __device__ __forceinline__ void combine_unit(const DecodeTmaParams& p, uint8_t* 
     constexpr int kVec = kD / 4;                                  // lanes per row: 32 (D 128) or 16 (D 64), 16 bytes each
     constexpr int kPerLane = 64 / kVec;                           // LSEs per lane (S <= 64)
     const int lane_in_row = tid % kVec;
-    const int row_bytes = S * kD * 4;
     const int rows_per_group = combine_rows_per_group(p, kD, ring_bytes, rows_here);
     float* stage = reinterpret_cast<float*>(smem);                // [rows of the group][S][kD]
     uint32_t parity = 0;
